@@ -1,0 +1,180 @@
+/*
+ * b200sparse.h — C ABI of libb200sparse.so, the B200 (sm_100a) sparse hot path.
+ *
+ * This header is the drop-in boundary.  The reference
+ * (nv-legate/legate-sparse @ 49271fa) exports exactly one C symbol,
+ *   void legate_sparse_perform_registration(void)      src/sparse/sparse_c.h:26
+ * and moves everything else through Legate task contexts, i.e. there is no
+ * per-operation C ABI upstream.  The entry points below are what the
+ * reference's per-op task variants would bind if they were plain C calls;
+ * each one cites the task (file:line) it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: raw DEVICE pointers, sizes, an opaque stream handle
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - every call is asynchronous on `stream` unless stated otherwise and
+ *     returns 0 on success or a non-zero B2S_ERR_* code (never aborts; the
+ *     reference aborts via assert(false), src/sparse/util/cuda_help.h:51-74);
+ *   - the caller owns every buffer (matrix arrays, vectors, workspaces);
+ *   - matrices are scipy-layout CSR: indptr[nrows+1] (int64), indices[nnz]
+ *     (int32 or int64, see b2s_itype), data[nnz].  The reference's
+ *     Rect<1>{lo,hi} `pos` packing (legate_sparse/csr.py:238-251) is a Legion
+ *     artifact and is not part of this boundary.
+ */
+#ifndef B200SPARSE_H
+#define B200SPARSE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_VERSION 100 /* 0.1.0 */
+
+/* value types = the reference's supported set (legate_sparse/utils.py:28-33,
+ * src/sparse/util/dispatch.h:33-48) */
+typedef enum { B2S_F32 = 0, B2S_F64 = 1, B2S_C64 = 2, B2S_C128 = 3 } b2s_dtype;
+/* column-index width (reference: int64 `coord_ty`, legate_sparse/types.py:20;
+ * dispatch.h:56-77 also instantiates int32) */
+typedef enum { B2S_I32 = 0, B2S_I64 = 1 } b2s_itype;
+
+enum {
+  B2S_OK              = 0,
+  B2S_ERR_ARG         = 1, /* bad argument (null pointer, negative size, bad enum) */
+  B2S_ERR_CUDA        = 2, /* a CUDA runtime call / launch failed */
+  B2S_ERR_WORKSPACE   = 3, /* caller workspace too small */
+  B2S_ERR_UNSUPPORTED = 4, /* dtype/itype combination not built */
+  B2S_ERR_OVERFLOW    = 5  /* hash table / size overflow */
+};
+
+typedef void* b2s_stream_t; /* cudaStream_t */
+
+int         b2s_version(void);
+const char* b2s_last_error_string(void); /* thread-local, valid until next call */
+/* number of kernels launched by this library in this process (bench `gpu_launches`) */
+int64_t     b2s_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * CSR SpMV  y = A x.          replaces CSRSpMVRowSplit::gpu_variant
+ *   src/sparse/array/csr/spmv.cu:30-163 (cuSPARSE SpMV) and the CPU/OMP loops
+ *   spmv.cc:36-43 / spmv_omp.cc:36-44.
+ *
+ * The local row block is [0,nrows); `x` is addressed with GLOBAL column ids
+ * (the reference shifts the x base pointer instead, spmv.cu:75-90).
+ *
+ * Plan = cached per-matrix tiling (the analogue of Legate's cached image
+ * partitions, csr.py:587-591): nnz-balanced tiles, the row that each tile
+ * starts in, and the [min col, max col] x-window of each tile (the
+ * reference's MIN_MAX image of crd→x).  Building a plan synchronises the
+ * stream once.  `plan` may be NULL: then the plan-free row-vector kernel runs.
+ * ---------------------------------------------------------------------- */
+typedef struct b2s_spmv_plan b2s_spmv_plan; /* opaque, host object */
+
+enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2 };
+
+/* bytes of device workspace a plan for this matrix needs */
+int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz);
+
+int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                         const int64_t* indptr, const void* indices,
+                         void* workspace, int64_t workspace_bytes,
+                         b2s_stream_t stream, b2s_spmv_plan** out_plan);
+void b2s_spmv_plan_destroy(b2s_spmv_plan* plan);
+/* introspection (tests / bench): number of tiles, nnz per tile, and how many
+ * tiles stage their x window in shared memory through the TMA bulk copy */
+int b2s_spmv_plan_info(const b2s_spmv_plan* plan, int64_t* ntiles, int64_t* tile_nnz,
+                       int64_t* window_tiles);
+
+int b2s_spmv_csr(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                 const int64_t* indptr, const void* indices, const void* data,
+                 const void* x, void* y, const b2s_spmv_plan* plan, int variant,
+                 b2s_stream_t stream);
+
+/* SpMV fused with a dot product:  y = A x;  dot_out[0] = sum_r w[r] * y[r]  (no conjugation).
+ * With w = x (+ the row offset of the block) this is the CG pair q=A.matvec(p); pq=p.dot(q)
+ * (linalg.py:519-520) in one pass.  `w` has nrows entries, `dot_out` is one device scalar of
+ * the value type.  Requires a plan (per-tile partials live in the plan workspace). */
+int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                     const int64_t* indptr, const void* indices, const void* data,
+                     const void* x, void* y, const void* w, const b2s_spmv_plan* plan,
+                     void* dot_out, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Dense vector kernels of the CG/GMRES loop.
+ * ---------------------------------------------------------------------- */
+/* AXPBY task: src/sparse/linalg/axpby.cu:25-66, axpby_template.inl:30-71.
+ *   val = a[0]/b[0] (device scalars), negated if `negate`;
+ *   isalpha: y = val*x + y   else: y = x + val*y                          */
+int b2s_axpby(b2s_dtype vt, int64_t n, void* y, const void* x, const void* a, const void* b,
+              int isalpha, int negate, b2s_stream_t stream);
+
+int64_t b2s_reduce_workspace_bytes(void);
+/* out[0] = sum_i conj?(x_i) * y_i  — numpy `x.dot(y)` semantics (NO conjugation),
+ * the reference calls cupynumeric r.dot(z) (linalg.py:510,520); conj=1 gives vdot. */
+int b2s_dot(b2s_dtype vt, int64_t n, const void* x, const void* y, int conj, void* out,
+            void* partials, b2s_stream_t stream);
+/* out[0] = ||x||_2 as the REAL type of vt (np.linalg.norm, linalg.py:482,529) */
+int b2s_nrm2(b2s_dtype vt, int64_t n, const void* x, void* out, void* partials,
+             b2s_stream_t stream);
+
+/* Fused CG vector update (identity preconditioner), one pass over x,r,p,q:
+ *   alpha = rho/pq;  x += alpha p;  r -= alpha q;  rr_out = <r,r>
+ * = the two cg_axpby calls + the next r.dot(z) of linalg.py:523-525,510.      */
+int b2s_cg_update(b2s_dtype vt, int64_t n, void* x, void* r, const void* p, const void* q,
+                  const void* rho, const void* pq, void* rr_out, void* partials,
+                  b2s_stream_t stream);
+/* p = r + (rho/rho1) p   (linalg.py:516-518 with z == r); rho1[0]==0 ⇒ p = r */
+int b2s_cg_pupdate(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
+                   const void* rho1, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * CSR x CSR SpGEMM  C = A B.   replaces SpGEMMCSRxCSRxCSRGPU
+ *   src/sparse/array/csr/spgemm_csr_csr_csr.cu:64-487 (cuSPARSE SpGEMM) and the
+ *   two-task CPU shape (NNZ task + numeric task, csr.py:687-744,
+ *   spgemm_csr_csr_csr.cc:62-87,134-158).
+ *
+ * Two phases because C is caller-allocated:
+ *   symbolic: row_nnz → c_indptr[nrowsA+1] (exclusive scan, c_indptr[nrowsA]=nnz(C)),
+ *             also returns nnz(C) and the number of intermediate products on the host
+ *             (synchronises the stream);
+ *   numeric : fills c_indices (sorted within each row, like cuSPARSE) and c_data.
+ * A block of rows of A may be passed (row-block partition); B is whole.
+ * ---------------------------------------------------------------------- */
+int64_t b2s_spgemm_workspace_bytes(int64_t nrowsA, int64_t nnzA, int64_t ncolsB);
+
+int b2s_spgemm_symbolic(b2s_itype it, int64_t nrowsA, int64_t ncolsA, int64_t ncolsB,
+                        const int64_t* a_indptr, const void* a_indices, int64_t nnzA,
+                        const int64_t* b_indptr, const void* b_indices, int64_t nnzB,
+                        int64_t* c_indptr, void* workspace, int64_t workspace_bytes,
+                        int64_t* out_nnzC, int64_t* out_products, b2s_stream_t stream);
+
+int b2s_spgemm_numeric(b2s_dtype vt, b2s_itype it, int64_t nrowsA, int64_t ncolsA,
+                       int64_t ncolsB, const int64_t* a_indptr, const void* a_indices,
+                       const void* a_data, int64_t nnzA, const int64_t* b_indptr,
+                       const void* b_indices, const void* b_data, int64_t nnzB,
+                       const int64_t* c_indptr, void* c_indices, void* c_data,
+                       void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Small CSR helpers on the path's edges (SURVEY §8f "next" rows).
+ * ---------------------------------------------------------------------- */
+/* GetCSRDiagonal: src/sparse/array/csr/get_diagonal.cu:25-44 */
+int b2s_csr_diagonal(b2s_dtype vt, b2s_itype it, int64_t nrows, const int64_t* indptr,
+                     const void* indices, const void* data, void* diag, b2s_stream_t stream);
+/* ExpandPosToCoordinates: src/sparse/array/conv/pos_to_coordinates_template.inl:46-112
+ * rows_out[j] = i for indptr[i] <= j < indptr[i+1] (int64) */
+int b2s_csr_expand_rows(int64_t nrows, int64_t nnz, const int64_t* indptr, int64_t* rows_out,
+                        b2s_stream_t stream);
+/* index width conversion (reference `cast` kernels, util/cusparse_utils.h:260-268) */
+int b2s_cast_i64_to_i32(int64_t n, const int64_t* src, int32_t* dst, b2s_stream_t stream);
+int b2s_cast_i32_to_i64(int64_t n, const int32_t* src, int64_t* dst, b2s_stream_t stream);
+/* CSRToDense (csr_to_dense.cu:25-47): out is row-major nrows x ncols, pre-zeroed by callee */
+int b2s_csr_to_dense(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols,
+                     const int64_t* indptr, const void* indices, const void* data, void* out,
+                     b2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARSE_H */

@@ -1,0 +1,237 @@
+"""Device-buffer plumbing: torch tensors as HBM buffers + typed wrappers over the C ABI.
+
+PyTorch is used ONLY for device memory, streams and (in dist.py) torch.distributed;
+all arithmetic on the hot path is done by libb200sparse kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int64, c_void_p, byref
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_NP2ENUM = {
+    np.dtype(np.float32): N.B2S_F32,
+    np.dtype(np.float64): N.B2S_F64,
+    np.dtype(np.complex64): N.B2S_C64,
+    np.dtype(np.complex128): N.B2S_C128,
+}
+_NP2TORCH = {
+    np.dtype(np.float32): torch.float32,
+    np.dtype(np.float64): torch.float64,
+    np.dtype(np.complex64): torch.complex64,
+    np.dtype(np.complex128): torch.complex128,
+    np.dtype(np.int32): torch.int32,
+    np.dtype(np.int64): torch.int64,
+    np.dtype(np.bool_): torch.bool,
+    np.dtype(np.uint8): torch.uint8,
+    np.dtype(np.int8): torch.int8,
+    np.dtype(np.int16): torch.int16,
+    np.dtype(np.float16): torch.float16,
+}
+_TORCH2NP = {v: k for k, v in _NP2TORCH.items()}
+
+
+def np_dtype_of(t) -> np.dtype:
+    if isinstance(t, torch.Tensor):
+        return _TORCH2NP[t.dtype]
+    return np.dtype(t.dtype)
+
+
+def torch_dtype(dt) -> torch.dtype:
+    return _NP2TORCH[np.dtype(dt)]
+
+
+def vt_enum(dt) -> int:
+    try:
+        return _NP2ENUM[np.dtype(dt)]
+    except KeyError:
+        raise NotImplementedError(f"dtype {dt} is not supported by the B200 kernels")
+
+
+def real_dtype(dt) -> np.dtype:
+    dt = np.dtype(dt)
+    return np.dtype(np.float32) if dt in (np.dtype(np.float32), np.dtype(np.complex64)) else np.dtype(np.float64)
+
+
+_checked = False
+
+
+def require_cuda() -> torch.device:
+    """Fail loudly when there is no GPU or no native library (never fall back to CPU)."""
+    global _checked
+    if not _checked:
+        N.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "legate_sparse (b200): no CUDA device is available; the sm_100a kernels are the "
+                "only compute path (there is no CPU fallback)."
+            )
+        _checked = True
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def is_device_tensor(x) -> bool:
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def to_device(x, dtype=None, copy=False) -> torch.Tensor:
+    """numpy / torch(cpu|cuda) → contiguous CUDA tensor (optionally cast)."""
+    dev = require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x
+        if not t.is_cuda:
+            t = t.to(dev, non_blocking=True)
+            copy = False
+    else:
+        a = np.ascontiguousarray(x)
+        t = torch.from_numpy(a).to(dev, non_blocking=False)
+        copy = False
+    if dtype is not None and t.dtype != torch_dtype(dtype):
+        t = t.to(torch_dtype(dtype))
+        copy = False
+    if not t.is_contiguous():
+        t = t.contiguous()
+        copy = False
+    if copy:
+        t = t.clone()
+    return t
+
+
+def to_host(t) -> np.ndarray:
+    if isinstance(t, torch.Tensor):
+        return t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def empty(n, dtype) -> torch.Tensor:
+    return torch.empty(int(n), dtype=torch_dtype(dtype), device=require_cuda())
+
+
+def zeros(n, dtype) -> torch.Tensor:
+    return torch.zeros(int(n), dtype=torch_dtype(dtype), device=require_cuda())
+
+
+# ------------------------------------------------------------------ reductions workspace
+_red_ws = {}
+
+
+def reduce_ws() -> torch.Tensor:
+    dev = require_cuda()
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _red_ws.get(key)
+    if ws is None:
+        nbytes = int(N.load().b2s_reduce_workspace_bytes())
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        _red_ws[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------ SpMV plan
+class SpmvPlan:
+    """Owner of a native b2s_spmv_plan + its device workspace (cached per matrix)."""
+
+    def __init__(self, itype, nrows, ncols, nnz, indptr, indices):
+        lib = N.load()
+        nbytes = int(lib.b2s_spmv_plan_workspace_bytes(nrows, nnz))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=indptr.device)
+        self.handle = c_void_p(0)
+        N.check(
+            lib.b2s_spmv_plan_create(
+                itype, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(self.ws), nbytes, stream_ptr(),
+                byref(self.handle),
+            ),
+            "spmv_plan_create",
+        )
+        self._lib = lib
+
+    def info(self):
+        a, b, c = c_int64(0), c_int64(0), c_int64(0)
+        N.check(self._lib.b2s_spmv_plan_info(self.handle, byref(a), byref(b), byref(c)), "spmv_plan_info")
+        return {"ntiles": a.value, "tile_nnz": b.value, "window_tiles": c.value}
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.b2s_spmv_plan_destroy(self.handle)
+                self.handle = c_void_p(0)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ typed wrappers
+def spmv(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan=None, variant=N.B2S_SPMV_AUTO):
+    N.check(
+        N.load().b2s_spmv_csr(
+            vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y),
+            plan.handle if plan is not None else c_void_p(0), variant, stream_ptr(),
+        ),
+        "spmv_csr",
+    )
+
+
+def spmv_dot(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, w, plan, dot_out):
+    N.check(
+        N.load().b2s_spmv_csr_dot(
+            vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), ptr(w),
+            plan.handle, ptr(dot_out), stream_ptr(),
+        ),
+        "spmv_csr_dot",
+    )
+
+
+def axpby(y, x, a, b, isalpha, negate):
+    vt = vt_enum(np_dtype_of(y))
+    N.check(
+        N.load().b2s_axpby(vt, y.numel(), ptr(y), ptr(x), ptr(a), ptr(b), int(bool(isalpha)), int(bool(negate)),
+                           stream_ptr()),
+        "axpby",
+    )
+
+
+def dot(x, y, conj=False, out=None):
+    dt = np_dtype_of(x)
+    if out is None:
+        out = empty(1, dt)
+    N.check(
+        N.load().b2s_dot(vt_enum(dt), x.numel(), ptr(x), ptr(y), int(conj), ptr(out), ptr(reduce_ws()),
+                         stream_ptr()),
+        "dot",
+    )
+    return out
+
+
+def nrm2(x, out=None):
+    dt = np_dtype_of(x)
+    if out is None:
+        out = empty(1, real_dtype(dt))
+    N.check(N.load().b2s_nrm2(vt_enum(dt), x.numel(), ptr(x), ptr(out), ptr(reduce_ws()), stream_ptr()), "nrm2")
+    return out
+
+
+def cg_update(x, r, p, q, rho, pq, rr_out):
+    dt = np_dtype_of(x)
+    N.check(
+        N.load().b2s_cg_update(vt_enum(dt), x.numel(), ptr(x), ptr(r), ptr(p), ptr(q), ptr(rho), ptr(pq),
+                               ptr(rr_out), ptr(reduce_ws()), stream_ptr()),
+        "cg_update",
+    )
+
+
+def cg_pupdate(p, r, rho, rho1):
+    dt = np_dtype_of(p)
+    N.check(N.load().b2s_cg_pupdate(vt_enum(dt), p.numel(), ptr(p), ptr(r), ptr(rho), ptr(rho1), stream_ptr()),
+            "cg_pupdate")

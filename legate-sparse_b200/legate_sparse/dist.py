@@ -1,0 +1,146 @@
+"""1-D row-block data parallelism, one process per GPU (torch.distributed: nccl on GPUs,
+gloo in CPU tests).
+
+The reference has exactly one strategy: Legate tiles the rows of A equally over
+the processors (``align(y, pos)``, /root/reference legate_sparse/csr.py:587-591), each GPU
+gets the contiguous crd/vals slice of its rows and the x window it needs; the only NCCL call
+upstream is a 1-element all-gather of per-GPU nnz (spgemm_csr_csr_csr.cu:43-62).
+
+Here: every rank runs the same script (SPMD).  A matrix is split into row blocks
+``bounds[r] .. bounds[r+1]``; x is replicated; each rank computes its block of y with the
+local sm_100a kernel and — when a replicated result is needed (CG/GMRES) — the blocks are
+all-gathered (NCCL over NVLink / NVSwitch).  Dense-vector reductions are done on the local
+block and all-reduced.
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+
+def is_initialized() -> bool:
+    return td.is_available() and td.is_initialized()
+
+
+def world_size() -> int:
+    return td.get_world_size() if is_initialized() else 1
+
+
+def rank() -> int:
+    return td.get_rank() if is_initialized() else 0
+
+
+def init(backend: str | None = None) -> None:
+    """Join the process group described by the torchrun environment (RANK/WORLD_SIZE/
+    MASTER_ADDR/MASTER_PORT/LOCAL_RANK).  No-op for a single process."""
+    if is_initialized() or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return
+    use_cuda = torch.cuda.is_available()
+    if backend is None:
+        backend = "nccl" if use_cuda else "gloo"
+    if use_cuda:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    td.init_process_group(backend=backend)
+
+
+def shutdown() -> None:
+    if is_initialized():
+        td.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------- partitions
+def row_block_bounds(nrows: int, nparts: int) -> np.ndarray:
+    """Equal-row tiling (what Legate's ``align(y, pos)`` produces): block = ceil(n/G)."""
+    nparts = max(int(nparts), 1)
+    block = -(-int(nrows) // nparts) if nrows > 0 else 0
+    b = np.minimum(np.arange(nparts + 1, dtype=np.int64) * block, nrows)
+    return b.astype(np.int64)
+
+
+def nnz_balanced_bounds(indptr, nparts: int) -> np.ndarray:
+    """Row boundaries with ~equal nnz per part (binary search on indptr) — for skewed
+    (power-law) matrices where equal rows starve some GPUs."""
+    ip = indptr.detach().cpu().numpy() if isinstance(indptr, torch.Tensor) else np.asarray(indptr)
+    nrows = ip.shape[0] - 1
+    nnz = int(ip[-1])
+    targets = (np.arange(1, nparts, dtype=np.float64) * (nnz / float(nparts))).astype(np.int64)
+    cuts = np.searchsorted(ip, targets, side="left").astype(np.int64)
+    b = np.concatenate([[0], np.clip(cuts, 0, nrows), [nrows]]).astype(np.int64)
+    return np.maximum.accumulate(b)
+
+
+# ---------------------------------------------------------------------------- collectives
+def allgather_rows(local: torch.Tensor, bounds: Sequence[int]) -> torch.Tensor:
+    """Gather the row blocks ``local`` (this rank owns rows bounds[rank]:bounds[rank+1])
+    into the full replicated vector.  Blocks may be ragged; they are padded to the largest
+    block so that a single all_gather_into_tensor (one NCCL all-gather) suffices."""
+    G = world_size()
+    n = int(bounds[-1])
+    if G == 1:
+        return local
+    sizes = [int(bounds[i + 1] - bounds[i]) for i in range(G)]
+    blk = max(sizes) if sizes else 0
+    if blk == 0:
+        return local.new_zeros(0)
+    send = local
+    if local.numel() != blk:
+        send = local.new_zeros(blk)
+        send[: local.numel()] = local
+    recv = local.new_empty(G * blk)
+    td.all_gather_into_tensor(recv, send.contiguous())
+    if all(s == blk for s in sizes):
+        return recv[:n] if G * blk != n else recv
+    out = local.new_empty(n)
+    for i in range(G):
+        if sizes[i]:
+            out[int(bounds[i]) : int(bounds[i + 1])] = recv[i * blk : i * blk + sizes[i]]
+    return out
+
+
+def allgather_into(full: torch.Tensor, bounds: Sequence[int]) -> torch.Tensor:
+    """In-place variant: ``full`` already holds this rank's block at its row offset; after the
+    call every rank holds every block.  Equal-size fast path needs no staging copy."""
+    G = world_size()
+    if G == 1:
+        return full
+    r = rank()
+    sizes = [int(bounds[i + 1] - bounds[i]) for i in range(G)]
+    blk = max(sizes)
+    n = int(bounds[-1])
+    if all(int(bounds[i]) == i * blk for i in range(G)) and G * blk == n:
+        td.all_gather_into_tensor(full, full[r * blk : (r + 1) * blk])
+        return full
+    gathered = allgather_rows(full[int(bounds[r]) : int(bounds[r + 1])], bounds)
+    full.copy_(gathered)
+    return full
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    if world_size() > 1:
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+    return t
+
+
+def allgather_varlen(local: torch.Tensor) -> tuple[torch.Tensor, np.ndarray]:
+    """all-gather(v) of 1-D tensors of different lengths: returns (concatenation in rank
+    order, per-rank counts).  Used for the SpGEMM C blocks; the count exchange is the
+    analogue of the reference's ncclAllGather of per-rank nnz (spgemm_csr_csr_csr.cu:43-62)."""
+    G = world_size()
+    if G == 1:
+        return local, np.array([local.numel()], dtype=np.int64)
+    cnt = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    cnts = torch.empty(G, dtype=torch.int64, device=local.device)
+    td.all_gather_into_tensor(cnts, cnt)
+    counts = cnts.cpu().numpy()
+    blk = int(counts.max())
+    send = local.new_zeros(blk)
+    send[: local.numel()] = local
+    recv = local.new_empty(G * blk)
+    td.all_gather_into_tensor(recv, send)
+    parts = [recv[i * blk : i * blk + int(counts[i])] for i in range(G)]
+    return torch.cat(parts), counts

@@ -1,0 +1,543 @@
+"""Iterative solvers and the LinearOperator family
+(reference /root/reference legate_sparse/linalg.py:85-668).
+
+The solver loops keep every vector in HBM as a CUDA tensor and every scalar (rho, pq, …) as
+a 1-element device array, exactly like the reference keeps them as Legate futures
+(linalg.py:440-445): the host only synchronises at the convergence test every
+``conv_test_iters`` iterations (linalg.py:529-533).
+
+Array convention: if ``b`` is a numpy array the result, the callback argument and the
+vectors handed to user-defined ``matvec`` callables are numpy arrays (drop-in for scipy
+code); if ``b`` is a CUDA ``torch.Tensor`` everything stays on the device.
+
+Fast path: ``cg`` with a ``csr_array`` A and no preconditioner runs three fused kernels per
+iteration (SpMV+p·q, x/r update + r·r, p update) instead of the reference's
+1 SpMV + 2 dots + 3 axpby + 1 copy; the recurrence and its floating-point operations are the
+same.  Set ``LEGATE_SPARSE_CG_UNFUSED=1`` to run the op-for-op reference sequence.
+"""
+from __future__ import annotations
+
+import inspect
+import os
+import warnings
+
+import numpy as np
+import torch
+
+from . import dist
+from . import _native as N
+
+
+def _is_dev(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _np_dtype(x):
+    from ._device import np_dtype_of
+
+    return np_dtype_of(x) if isinstance(x, torch.Tensor) else np.dtype(x.dtype)
+
+
+# ======================================================================= LinearOperator
+class LinearOperator:
+    """Common interface for matrix-vector products (scipy.sparse.linalg.LinearOperator
+    shape; reference linalg.py:85-302).  Subclasses implement ``_matvec(x, out=None)``."""
+
+    ndim = 2
+
+    def __new__(cls, *args, **kwargs):
+        if cls is LinearOperator:
+            # Operate as _CustomLinearOperator factory.
+            return super(LinearOperator, cls).__new__(_CustomLinearOperator)
+        obj = super(LinearOperator, cls).__new__(cls)
+        if type(obj)._matvec == LinearOperator._matvec and type(obj)._matmat == LinearOperator._matmat:
+            warnings.warn(
+                "LinearOperator subclass should implement at least one of _matvec and _matmat.",
+                category=RuntimeWarning,
+                stacklevel=2,
+            )
+        return obj
+
+    def __init__(self, dtype, shape):
+        if dtype is not None:
+            dtype = np.dtype(dtype)
+        self.dtype = dtype
+        self.shape = tuple(shape)
+
+    def _init_dtype(self):
+        """Called from subclasses at the end of __init__: infer dtype from matvec(zeros)."""
+        if self.dtype is None:
+            v = np.zeros(self.shape[-1])
+            self.dtype = _np_dtype(self.matvec(v))
+
+    def _matmat(self, X):
+        raise NotImplementedError
+
+    def _matvec(self, x, out=None):
+        raise NotImplementedError
+
+    def matvec(self, x, out=None):
+        M, Ncols = self.shape
+        if tuple(x.shape) != (Ncols,) and tuple(x.shape) != (Ncols, 1):
+            raise ValueError("dimension mismatch")
+        y = self._matvec(x, out=out)
+        if not isinstance(y, torch.Tensor):
+            y = np.asarray(y)
+        if x.ndim == 1:
+            y = y.reshape((M,))
+        elif x.ndim == 2:
+            y = y.reshape(M, 1)
+        else:
+            raise ValueError("invalid shape returned by user-defined matvec()")
+        return y
+
+    def _rmatvec(self, x, out=None):
+        raise NotImplementedError
+
+    def rmatvec(self, x, out=None):
+        M, Ncols = self.shape
+        if tuple(x.shape) != (M,) and tuple(x.shape) != (M, 1):
+            raise ValueError("dimension mismatch")
+        y = self._rmatvec(x, out=out)
+        if not isinstance(y, torch.Tensor):
+            y = np.asarray(y)
+        if x.ndim == 1:
+            y = y.reshape(Ncols)
+        elif x.ndim == 2:
+            y = y.reshape(Ncols, 1)
+        else:
+            raise ValueError("invalid shape returned by user-defined rmatvec()")
+        return y
+
+
+class _CustomLinearOperator(LinearOperator):
+    """Linear operator defined by user callables (reference linalg.py:307-363): the ``out=``
+    keyword is forwarded only when the callable's signature has it."""
+
+    def __init__(self, shape, matvec, rmatvec=None, matmat=None, dtype=None, rmatmat=None):
+        super().__init__(dtype, shape)
+        self.args = ()
+        self.__matvec_impl = matvec
+        self.__rmatvec_impl = rmatvec
+        self._matvec_has_out = self._has_out(self.__matvec_impl)
+        self._rmatvec_has_out = self._has_out(self.__rmatvec_impl)
+        self._init_dtype()
+
+    def _matvec(self, x, out=None):
+        if self._matvec_has_out:
+            return self.__matvec_impl(x, out=out)
+        if out is None:
+            return self.__matvec_impl(x)
+        res = self.__matvec_impl(x)
+        _assign(out, res)
+        return out
+
+    def _rmatvec(self, x, out=None):
+        func = self.__rmatvec_impl
+        if func is None:
+            raise NotImplementedError("rmatvec is not defined")
+        if self._rmatvec_has_out:
+            return func(x, out=out)
+        if out is None:
+            return func(x)
+        _assign(out, func(x))
+        return out
+
+    def _has_out(self, o):
+        if o is None:
+            return False
+        return "out" in inspect.signature(o).parameters
+
+
+def _assign(out, res):
+    """out[:] = res across numpy / torch combinations."""
+    if isinstance(out, torch.Tensor):
+        if not isinstance(res, torch.Tensor):
+            res = torch.from_numpy(np.ascontiguousarray(res))
+        out.copy_(res.reshape(out.shape))
+    else:
+        if isinstance(res, torch.Tensor):
+            res = res.detach().cpu().numpy()
+        out[:] = np.asarray(res).reshape(out.shape)
+
+
+class _SparseMatrixLinearOperator(LinearOperator):
+    """Wraps a sparse matrix; caches the conjugate transpose (reference linalg.py:369-387)."""
+
+    def __init__(self, A):
+        self.A = A
+        self.AH = None
+        super().__init__(A.dtype, A.shape)
+
+    def _matvec(self, x, out=None):
+        return self.A.dot(x, out=out)
+
+    def _rmatvec(self, x, out=None):
+        if self.AH is None:
+            self.AH = self.A.T.conj(copy=False)
+        return self.AH.dot(x, out=out)
+
+
+class IdentityOperator(LinearOperator):
+    def __init__(self, shape, dtype=None):
+        super().__init__(dtype, shape)
+
+    def _matvec(self, x, out=None):
+        if out is not None:
+            _assign(out, x)
+            return out
+        return x.clone() if isinstance(x, torch.Tensor) else x.copy()
+
+    def _rmatvec(self, x, out=None):
+        return self._matvec(x, out=out)
+
+
+def make_linear_operator(A):
+    if isinstance(A, LinearOperator):
+        return A
+    return _SparseMatrixLinearOperator(A)
+
+
+# ======================================================================= cg_axpby
+def _scalar_dev(a, dtype):
+    """0-d / 1-element array or python scalar → 1-element device tensor of `dtype`."""
+    from ._device import to_device, torch_dtype
+
+    if _is_dev(a):
+        a = a.reshape(-1)[:1]
+        return a if a.dtype == torch_dtype(dtype) else a.to(torch_dtype(dtype))
+    return to_device(np.asarray(a, dtype=dtype).reshape(-1)[:1])
+
+
+def cg_axpby(y, x, a, b, isalpha=True, negate=False):
+    """y = alpha*x + beta*y with alpha or beta = (+/-) a/b computed ON THE DEVICE from the
+    1-element arrays a, b (reference linalg.py:433-451, AXPBY task axpby.cu:25-47):
+    isalpha → y = (a/b)*x + y, else y = x + (a/b)*y.  Updates y in place and returns it."""
+    from ._device import axpby as _axpby
+    from ._device import to_device, to_host
+
+    dt = _np_dtype(y)
+    if _is_dev(y):
+        _axpby(y, to_device(x, dtype=dt), _scalar_dev(a, dt), _scalar_dev(b, dt), isalpha, negate)
+        return y
+    yd = to_device(y)
+    _axpby(yd, to_device(x, dtype=dt), _scalar_dev(a, dt), _scalar_dev(b, dt), isalpha, negate)
+    y[...] = to_host(yd).reshape(y.shape)
+    return y
+
+
+def _get_atol_rtol(b_norm, tol=None, atol=0.0, rtol=1e-5):
+    rtol = float(tol) if tol is not None else rtol
+    if atol is None:
+        atol = rtol
+    atol = max(float(atol), float(rtol) * float(b_norm))
+    return atol, rtol
+
+
+# ======================================================================= device-side operators
+class _DevOp:
+    """Uniform device-side view ``apply(x_dev, out_dev) -> y_dev`` of a LinearOperator."""
+
+    def __init__(self, op, numpy_mode):
+        self.op = op
+        self.numpy_mode = numpy_mode
+        self.is_identity = isinstance(op, IdentityOperator)
+        self.csr = op.A if isinstance(op, _SparseMatrixLinearOperator) else None
+
+    def apply(self, x, out=None):
+        from ._device import to_device, to_host
+
+        if self.is_identity:
+            if out is None:
+                return x.clone()
+            out.copy_(x)
+            return out
+        if self.csr is not None:
+            from .csr import spmv
+
+            A = self.csr
+            if _np_dtype(x) != A.dtype:
+                A = A.astype(np.result_type(A.dtype, _np_dtype(x)), copy=False)
+                self.csr = A
+            return spmv(A, x, out)
+        if self.numpy_mode:
+            y = self.op.matvec(to_host(x))
+            y = to_device(y, dtype=_np_dtype(x))
+            if out is None:
+                return y
+            out.copy_(y)
+            return out
+        y = self.op.matvec(x, out=out)
+        if out is not None and y is not out:
+            out.copy_(y)
+            return out
+        return y
+
+
+def _vec_in(v, dtype):
+    """user vector → contiguous 1-D device tensor of dtype (copy)."""
+    from ._device import to_device
+
+    return to_device(v, dtype=dtype).reshape(-1)
+
+
+def _vec_out(t, like):
+    from ._device import to_host
+
+    if _is_dev(like):
+        return t.reshape(like.shape) if like.ndim == 2 else t
+    h = to_host(t)
+    if isinstance(like, torch.Tensor):
+        return torch.from_numpy(h).reshape(like.shape)
+    return h.reshape(like.shape) if like.ndim == 2 else h
+
+
+# ======================================================================= CG
+def cg(
+    A,
+    b,
+    x0=None,
+    tol=None,
+    maxiter=None,
+    M=None,
+    callback=None,
+    atol=0.0,
+    rtol=1e-5,
+    conv_test_iters=25,
+):
+    """Preconditioned conjugate gradient (reference linalg.py:465-535; returns ``(x, iters)``
+    — NOT scipy's ``(x, info)`` — and tests convergence only every ``conv_test_iters``
+    iterations and at ``maxiter-1``)."""
+    from . import _device as D
+
+    assert len(b.shape) == 1 or (len(b.shape) == 2 and b.shape[1] == 1)
+    assert len(A.shape) == 2 and A.shape[0] == A.shape[1]
+
+    numpy_mode = not _is_dev(b)
+    A_op = make_linear_operator(A)
+    dtype = np.result_type(A_op.dtype if A_op.dtype is not None else np.float64, _np_dtype(b))
+    if dtype not in (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.complex64), np.dtype(np.complex128)):
+        dtype = np.dtype(np.float64)
+
+    n = b.shape[0]
+    b_dev = D.to_device(b, dtype=dtype).reshape(-1)
+    bnrm2 = float(D.nrm2(b_dev).item())
+    atol, _ = _get_atol_rtol(bnrm2, tol, atol, rtol)
+    if maxiter is None:
+        maxiter = n * 10
+
+    M_op = IdentityOperator(A_op.shape, dtype=A_op.dtype) if M is None else make_linear_operator(M)
+    Ad, Md = _DevOp(A_op, numpy_mode), _DevOp(M_op, numpy_mode)
+
+    x = D.zeros(n, dtype) if x0 is None else _vec_in(x0, dtype).clone()
+
+    fused_ok = (
+        Ad.csr is not None
+        and Md.is_identity
+        and os.environ.get("LEGATE_SPARSE_CG_UNFUSED", "0") in ("0", "")
+        and Ad.csr.dtype == dtype
+    )
+    if fused_ok:
+        x, iters = _cg_fused(Ad.csr, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, numpy_mode)
+        return _vec_out(x, b), iters
+
+    # ---- op-for-op reference sequence (any operator / preconditioner) ----
+    p = D.zeros(n, dtype)
+    r = b_dev - Ad.apply(x)  # b - A x0
+    iters = 0
+    rho = D.zeros(1, dtype)
+    rho1 = D.zeros(1, dtype)
+    pq = D.zeros(1, dtype)
+    z = None
+    q = None
+    while iters < maxiter:
+        z = Md.apply(r, out=z)
+        rho1, rho = rho, rho1
+        D.dot(r, z, out=rho)
+        if iters == 0:
+            p.copy_(z)
+        else:
+            # p = z + (rho/rho1) p
+            D.axpby(p, z, rho, rho1, False, False)
+        q = Ad.apply(p, out=q)
+        D.dot(p, q, out=pq)
+        D.axpby(x, p, rho, pq, True, False)   # x += (rho/pq) p
+        D.axpby(r, q, rho, pq, True, True)    # r -= (rho/pq) q
+        iters += 1
+        if callback is not None:
+            callback(D.to_host(x) if numpy_mode else x)
+        if (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(D.nrm2(r).item()) < atol:
+            break
+    return _vec_out(x, b), iters
+
+
+def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, numpy_mode):
+    """Identity-preconditioned CG on row-block-local vectors with fused kernels.
+
+    Per iteration (G = number of ranks):
+      p_loc  = r_loc + (rho/rho1) p_loc            cg_pupdate        (p_full all-gathered if G>1)
+      q_loc  = A_blk p_full ; pq = <p_loc, q_loc>   spmv_csr_dot      (+ all-reduce if G>1)
+      x_loc += a p_loc ; r_loc -= a q_loc ; rr=<r,r> cg_update         (+ all-reduce if G>1)
+    The next rho is rr (z == r for the identity preconditioner)."""
+    from . import _device as D
+    from .csr import _spmv_block
+
+    G = dist.world_size()
+    n = A.shape[0]
+    blk = A._block()
+    bounds = A.row_bounds()
+    r0, r1 = blk.r0, blk.r1
+    plan = A._plan(blk)
+    vt = D.vt_enum(dtype)
+    cplx = dtype.kind == "c"
+
+    # r = b - A x0
+    p_full = D.zeros(n, dtype)
+    p_loc = p_full[r0:r1]
+    q = D.empty(r1 - r0, dtype)
+    x_loc = x[r0:r1] if G > 1 else x
+    if G > 1:
+        x_loc = x_loc.clone()
+    if bool(torch.any(x != 0).item()) if x.numel() else False:
+        _spmv_block(A, blk, x, q)
+        r = b_dev[r0:r1] - q
+    else:
+        r = b_dev[r0:r1].clone()
+
+    rho = D.zeros(1, dtype)
+    rho1 = D.zeros(1, dtype)   # 0 ⇒ first cg_pupdate does p = r
+    pq = D.zeros(1, dtype)
+    rr = D.zeros(1, dtype)
+    D.dot(r, r, out=rho)
+    dist.allreduce_sum_(rho)
+    iters = 0
+    while iters < maxiter:
+        D.cg_pupdate(p_loc, r, rho, rho1)
+        if G > 1:
+            dist.allgather_into(p_full, bounds)
+        if plan is not None:
+            D.spmv_dot(vt, blk.itype, blk.nrows, A.shape[1], blk.nnz, blk.indptr, blk.indices, blk.data,
+                       p_full, q, p_loc, plan, pq)
+        else:  # empty block
+            q.zero_()
+            pq.zero_()
+        dist.allreduce_sum_(pq)
+        D.cg_update(x_loc, r, p_loc, q, rho, pq, rr)
+        dist.allreduce_sum_(rr)
+        rho1, rho, rr = rho, rr, rho1   # rotate: new rho = rr ; old rho → rho1 ; recycle buffer
+        iters += 1
+        if callback is not None:
+            xf = dist.allgather_rows(x_loc, bounds) if G > 1 else x_loc
+            callback(D.to_host(xf) if numpy_mode else xf)
+        if iters % conv_test_iters == 0 or iters == (maxiter - 1):
+            if cplx:
+                nr2 = D.nrm2(r) ** 2
+                dist.allreduce_sum_(nr2)
+                rnorm = float(torch.sqrt(nr2).item())
+            else:
+                rnorm = float(torch.sqrt(rho.abs()).item())
+            if rnorm < atol:
+                break
+    x_out = dist.allgather_rows(x_loc, bounds) if G > 1 else x_loc
+    return x_out, iters
+
+
+# ======================================================================= GMRES
+def gmres(
+    A,
+    b,
+    x0=None,
+    tol=None,
+    restart=None,
+    maxiter=None,
+    M=None,
+    callback=None,
+    restrt=None,
+    atol=0.0,
+    callback_type=None,
+    rtol=1e-5,
+):
+    """Restarted GMRES with classical Gram-Schmidt (reference linalg.py:540-668, itself the
+    CuPy algorithm).  Returns ``(x, info)``.  SpMV and norms run on the B200 kernels; the
+    tall-skinny ``V^H u`` / ``V y`` products are library GEMVs on the device and the
+    (restart+1) x restart least-squares problem is solved on the host, as upstream."""
+    from . import _device as D
+
+    assert len(b.shape) == 1 or (len(b.shape) == 2 and b.shape[1] == 1)
+    assert len(A.shape) == 2 and A.shape[0] == A.shape[1]
+    assert restrt is None or not restart
+    if restrt is not None:
+        restart = restrt
+
+    numpy_mode = not _is_dev(b)
+    A_op = make_linear_operator(A)
+    n = A_op.shape[0]
+    M_op = IdentityOperator(A_op.shape, dtype=A_op.dtype) if M is None else make_linear_operator(M)
+    dtype = np.result_type(A_op.dtype if A_op.dtype is not None else np.float64, _np_dtype(b))
+    if dtype.kind not in "fc":
+        dtype = np.dtype(np.float64)
+    Ad, Md = _DevOp(A_op, numpy_mode), _DevOp(M_op, numpy_mode)
+    tdt = D.torch_dtype(dtype)
+
+    b_dev = D.to_device(b, dtype=dtype).reshape(-1)
+    x = D.zeros(n, dtype) if x0 is None else _vec_in(x0, dtype).clone()
+
+    bnrm2 = float(D.nrm2(b_dev).item())
+    atol, _ = _get_atol_rtol(bnrm2, tol, atol, rtol)
+    b_norm = bnrm2
+
+    if maxiter is None:
+        maxiter = n * 10
+    if restart is None:
+        restart = 20
+    restart = min(restart, n)
+    if callback_type is None:
+        callback_type = "pr_norm"
+    if callback_type not in ("x", "pr_norm"):
+        raise ValueError("Unknown callback_type: {}".format(callback_type))
+    if callback is None:
+        callback_type = None
+
+    dev = b_dev.device
+    V = torch.empty((n, restart), dtype=tdt, device=dev)
+    H = torch.zeros((restart + 1, restart), dtype=tdt, device=dev)
+    e = np.zeros((restart + 1,), dtype=dtype)
+
+    iters = 0
+    while True:
+        mx = Md.apply(x)
+        r = b_dev - Ad.apply(mx)
+        r_norm = float(D.nrm2(r).item())
+        if callback_type == "x":
+            callback(D.to_host(mx) if numpy_mode else mx)
+        elif callback_type == "pr_norm" and iters > 0:
+            callback(r_norm / b_norm)
+        if r_norm <= atol or iters >= maxiter:
+            break
+        v = r / r_norm
+        V[:, 0] = v
+        e[0] = r_norm
+
+        # Arnoldi iteration
+        for j in range(restart):
+            z = Md.apply(v)
+            u = Ad.apply(z)
+            Vj = V[:, : j + 1]
+            h = Vj.conj().T @ u
+            u = u - Vj @ h
+            H[: j + 1, j] = h
+            hn = D.nrm2(u)
+            H[j + 1, j] = hn[0]
+            if j + 1 < restart:
+                v = u / hn[0]
+                V[:, j + 1] = v
+
+        # least squares H y = e on the host (small)
+        y = np.linalg.lstsq(D.to_host(H), e, rcond=None)[0]
+        x = x + V @ D.to_device(np.ascontiguousarray(y), dtype=dtype)
+        iters += restart
+
+    info = 0
+    if iters == maxiter and not (r_norm <= atol):
+        info = iters
+    return _vec_out(mx, b), info
