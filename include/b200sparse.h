@@ -71,7 +71,13 @@ int64_t     b2s_launch_count(void);
  * ---------------------------------------------------------------------- */
 typedef struct b2s_spmv_plan b2s_spmv_plan; /* opaque, host object */
 
-enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2 };
+/* AUTO: MERGE when a plan is given and the arrays are 16-byte aligned, else TILE, else ROWVEC.
+ * MERGE  = persistent kernel, (col,val,indptr[,x window]) streamed by TMA bulk copies into a shared-
+ *          memory ring by a producer warp; consumers are nnz-balanced per lane + warp segmented scan
+ * PIPE   = same TMA ring, consumers walk one row per lane group (kept for A/B measurements)
+ * TILE   = one CTA per tile, register-staged 128-bit loads (fallback for unaligned slices)
+ * ROWVEC = plan-free 2..32 lanes per row */
+enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2, B2S_SPMV_PIPE = 3, B2S_SPMV_MERGE = 4 };
 
 /* bytes of device workspace a plan for this matrix needs */
 int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz);

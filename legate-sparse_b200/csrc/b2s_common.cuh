@@ -125,6 +125,22 @@ __device__ __forceinline__ c64 vshfl_xor(c64 v, int m) {
 __device__ __forceinline__ c128 vshfl_xor(c128 v, int m) {
   return c128{__shfl_xor_sync(0xffffffffu, v.re, m), __shfl_xor_sync(0xffffffffu, v.im, m)};
 }
+__device__ __forceinline__ float  vshfl_up(float v, int d)  { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double vshfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ c64 vshfl_up(c64 v, int d) {
+  return c64{__shfl_up_sync(0xffffffffu, v.re, d), __shfl_up_sync(0xffffffffu, v.im, d)};
+}
+__device__ __forceinline__ c128 vshfl_up(c128 v, int d) {
+  return c128{__shfl_up_sync(0xffffffffu, v.re, d), __shfl_up_sync(0xffffffffu, v.im, d)};
+}
+__device__ __forceinline__ float  vshfl_idx(float v, int l)  { return __shfl_sync(0xffffffffu, v, l); }
+__device__ __forceinline__ double vshfl_idx(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+__device__ __forceinline__ c64 vshfl_idx(c64 v, int l) {
+  return c64{__shfl_sync(0xffffffffu, v.re, l), __shfl_sync(0xffffffffu, v.im, l)};
+}
+__device__ __forceinline__ c128 vshfl_idx(c128 v, int l) {
+  return c128{__shfl_sync(0xffffffffu, v.re, l), __shfl_sync(0xffffffffu, v.im, l)};
+}
 __device__ __forceinline__ float  vshfl_down(float v, int d)  { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double vshfl_down(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ c64 vshfl_down(c64 v, int d) {

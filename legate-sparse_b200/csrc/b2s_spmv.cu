@@ -21,7 +21,7 @@
 namespace b2s {
 
 constexpr int kTileThreads = 256;
-constexpr int kWinCap      = 2048;  // x-window capacity in elements
+constexpr int kWinCap      = 1024;  // x-window capacity in elements (== kPipeWinCap)
 
 struct PlanHeader {  // host-side plan object
   b2s_itype it;
@@ -34,6 +34,9 @@ struct PlanHeader {  // host-side plan object
   int64_t* tile_win;   // [2*ntiles]  (aligned base col, count) ; count==0 → no window
   void*    head;       // [ntiles] * 16 bytes
   void*    dotp;       // [ntiles] * 16 bytes (per-tile partials of the fused dot)
+  void*    sub_head;   // [ntiles*8] * 16 bytes  (merge kernel: per-warp-sub-tile head pieces)
+  int64_t* sub_head_row;  // [ntiles*8]          (row*2+first_continuation, or -1)
+  int64_t  empty_rows; // number of rows without non-zeros
   int64_t* counters;   // [4]
 };
 
@@ -43,14 +46,11 @@ struct b2s_spmv_plan : b2s::PlanHeader {};
 
 namespace b2s {
 
-static int64_t default_tile_nnz() {
-  static int64_t v = [] {
-    const char* e = getenv("B2S_SPMV_TILE_NNZ");
-    int64_t t = e ? atoll(e) : 2048;
-    if (t != 1024 && t != 2048 && t != 4096) t = 2048;
-    return t;
-  }();
-  return v;
+static int64_t default_tile_nnz() {  // read at every plan creation (tools/spmv_sweep varies it)
+  const char* e = getenv("B2S_SPMV_TILE_NNZ");
+  int64_t t = e ? atoll(e) : 2048;
+  if (t != 1024 && t != 2048 && t != 4096) t = 2048;
+  return t;
 }
 
 // ------------------------------------------------------------------ plan kernels
@@ -106,6 +106,15 @@ __global__ void plan_tile_window_kernel(int64_t nnz, int64_t ntiles, int64_t til
     int64_t r0 = tile_row[t];
     if (indptr[r0] < S) atomicAdd((unsigned long long*)&counters[1], 1ull);
   }
+}
+
+__global__ void plan_count_empty_kernel(int64_t nrows, const int64_t* __restrict__ indptr,
+                                        int64_t* __restrict__ counters) {
+  int64_t cnt = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x)
+    cnt += (indptr[r + 1] == indptr[r]);
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd((unsigned long long*)&counters[2], (unsigned long long)cnt);
 }
 
 // ------------------------------------------------------------------ helpers
@@ -317,7 +326,115 @@ spmv_rowvec_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const I* _
   }
 }
 
+}  // namespace b2s
+#include "b2s_spmv_pipe.cuh"
+#include "b2s_spmv_merge.cuh"
+namespace b2s {
+
 // ------------------------------------------------------------------ host launchers
+static int num_sms() {
+  static int n = [] {
+    int dev = 0, v = kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : kNumSMs;
+  }();
+  return n;
+}
+
+template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool ROWWALK>
+static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
+                            const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
+                            cudaStream_t st) {
+  using L = PipeLayout<V, I, IPT>;
+  const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
+  auto kern = spmv_pipe_kernel<V, I, IPT, STAGES, WINDOW, DOT, ROWWALK>;
+  static int blocks_per_sm = -1;  // per instantiation
+  if (blocks_per_sm < 0) {
+    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
+    if (nb < 1) { set_error("spmv_pipe_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
+    blocks_per_sm = nb;
+  }
+  int64_t grid = (int64_t)blocks_per_sm * num_sms();
+  if (grid > P->ntiles) grid = P->ntiles;
+  *npartials = grid;
+  kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals,
+                                                   x, y, P->tile_row, P->tile_win,
+                                                   reinterpret_cast<V*>(P->head), dot_partials, w);
+  B2S_CHECK_LAUNCH();
+  return B2S_OK;
+}
+
+template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT>
+static int launch_merge_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
+                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
+                             cudaStream_t st) {
+  using L = PipeLayout<V, I, IPT>;
+  const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
+  auto kern = spmv_merge_kernel<V, I, IPT, STAGES, WINDOW, DOT>;
+  static int blocks_per_sm = -1;  // per instantiation
+  if (blocks_per_sm < 0) {
+    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
+    if (nb < 1) { set_error("spmv_merge_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
+    blocks_per_sm = nb;
+  }
+  int64_t grid = (int64_t)blocks_per_sm * num_sms();
+  if (grid > P->ntiles) grid = P->ntiles;
+  *npartials = grid;
+  kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles,
+                                                   P->empty_rows > 0 ? 1 : 0, indptr, cols, vals, x, y,
+                                                   P->tile_row, P->tile_win, reinterpret_cast<V*>(P->sub_head),
+                                                   P->sub_head_row, dot_partials, w);
+  B2S_CHECK_LAUNCH();
+  const int64_t nsub = P->ntiles * (kPipeConsumers / 32);
+  spmv_subfixup_kernel<V><<<(unsigned)ceil_div(nsub, 256), 256, 0, st>>>(
+      nsub, P->sub_head_row, reinterpret_cast<const V*>(P->sub_head), y);
+  B2S_CHECK_LAUNCH();
+  return B2S_OK;
+}
+
+static int pipe_stages_default(int ipt) {
+  const char* e = getenv("B2S_SPMV_STAGES");
+  int s = e ? atoi(e) : (ipt == 4 ? 3 : 2);
+  return (s < 2 || s > 4) ? 2 : s;
+}
+
+template <typename V, typename I, int IPT, bool DOT>
+static int launch_pipe_ipt(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
+                           const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
+                           cudaStream_t st) {
+  bool window = (P->window_tiles * 2 >= P->ntiles) && ((uintptr_t)x % 16 == 0) &&
+                getenv("B2S_SPMV_NO_WINDOW") == nullptr;
+  // window matrices (banded / stencil): row-walk consumer; others: products consumer.
+  // Only STAGES = 2 is instantiated (deeper rings cost CTAs/SM and measured slower).
+  const bool rowwalk = window ? (getenv("B2S_SPMV_PRODUCTS") == nullptr) : (getenv("B2S_SPMV_ROWWALK") != nullptr);
+#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, 2, W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, st)
+  if (window) return rowwalk ? B2S_PIPE(true, true) : B2S_PIPE(true, false);
+  return rowwalk ? B2S_PIPE(false, true) : B2S_PIPE(false, false);
+#undef B2S_PIPE
+}
+
+template <typename V, typename I, int IPT, bool DOT>
+static int launch_merge_ipt(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
+                            const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
+                            cudaStream_t st) {
+  bool window = (P->window_tiles * 2 >= P->ntiles) && ((uintptr_t)x % 16 == 0) &&
+                getenv("B2S_SPMV_NO_WINDOW") == nullptr;
+#define B2S_MRG(W) launch_merge_inst<V, I, IPT, 2, W, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, st)
+  if (window) return B2S_MRG(true);
+  return B2S_MRG(false);
+#undef B2S_MRG
+}
+
+// pipe kernel needs 16-byte aligned streams (TMA bulk copies) and a 1024/2048 tile
+static bool pipe_ok(const PlanHeader* P, const void* indptr, const void* cols, const void* vals) {
+  return (P->tile_nnz == 1024 || P->tile_nnz == 2048) && ((uintptr_t)cols % 16 == 0) &&
+         ((uintptr_t)vals % 16 == 0) && ((uintptr_t)indptr % 16 == 0);
+}
+
 template <typename V, typename I, int IPT, bool VEC, bool WINDOW, bool DOT>
 static int launch_tile_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, cudaStream_t st) {
@@ -352,8 +469,22 @@ static int launch_tile_ipt(const PlanHeader* P, const int64_t* indptr, const I* 
 
 template <typename V, typename I, bool DOT>
 static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
-                    const V* x, V* y, V* dot_out, V* dot_partials, const V* w, cudaStream_t st) {
+                    const V* x, V* y, V* dot_out, V* dot_partials, const V* w, int mode, cudaStream_t st) {
   int rc;
+  int64_t npartials = P->ntiles;
+  if (mode == 2) {
+    if (P->tile_nnz == 1024) rc = launch_merge_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
+    else                     rc = launch_merge_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
+    if (rc) return rc;
+    if (DOT) {
+      reduce_partials_kernel<V><<<1, 1024, 0, st>>>(npartials, dot_partials, dot_out);
+      B2S_CHECK_LAUNCH();
+    }
+    return B2S_OK;   // the merge path has its own fix-up (sub-tile granularity)
+  } else if (mode == 1) {
+    if (P->tile_nnz == 1024) rc = launch_pipe_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
+    else                     rc = launch_pipe_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
+  } else
   switch (P->tile_nnz) {
     case 1024: rc = launch_tile_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, st); break;
     case 2048: rc = launch_tile_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, st); break;
@@ -368,7 +499,7 @@ static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, c
     B2S_CHECK_LAUNCH();
   }
   if (DOT) {
-    reduce_partials_kernel<V><<<1, 1024, 0, st>>>(P->ntiles, dot_partials, dot_out);
+    reduce_partials_kernel<V><<<1, 1024, 0, st>>>(npartials, dot_partials, dot_out);
     B2S_CHECK_LAUNCH();
   }
   return B2S_OK;
@@ -420,9 +551,9 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
     if (want_dot) { fill_zero_kernel<V><<<1, 32, 0, st>>>(1, dot_out); B2S_CHECK_LAUNCH(); }
     return B2S_OK;
   }
-  bool use_tile = (P != nullptr) && (variant == B2S_SPMV_AUTO || variant == B2S_SPMV_TILE);
-  if (variant == B2S_SPMV_TILE && P == nullptr) {
-    set_error("B2S_SPMV_TILE requires a plan");
+  bool use_tile = (P != nullptr) && (variant != B2S_SPMV_ROWVEC);
+  if ((variant == B2S_SPMV_TILE || variant == B2S_SPMV_PIPE || variant == B2S_SPMV_MERGE) && P == nullptr) {
+    set_error("B2S_SPMV_TILE / B2S_SPMV_PIPE require a plan");
     return B2S_ERR_ARG;
   }
   if (want_dot && !use_tile) {
@@ -434,8 +565,15 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
       set_error("plan does not match matrix (nrows/ncols/nnz/itype)");
       return B2S_ERR_ARG;
     }
-    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, st);
-    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, st);
+    const bool tma_ok = pipe_ok(P, indptr, cols, vals);
+    if ((variant == B2S_SPMV_PIPE || variant == B2S_SPMV_MERGE) && !tma_ok) {
+      set_error("B2S_SPMV_PIPE/MERGE need 16-byte aligned indptr/indices/data and a 1024/2048-nnz plan");
+      return B2S_ERR_ARG;
+    }
+    int mode = 0;
+    if (tma_ok && variant != B2S_SPMV_TILE) mode = (variant == B2S_SPMV_MERGE) ? 2 : 1;
+    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, st);
+    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, st);
   }
   return run_rowvec<V, I>(nrows, nnz, indptr, cols, vals, x, y, st);
 }
@@ -450,7 +588,7 @@ extern "C" int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz) {
   if (nnz < 0) return -1;
   int64_t ntiles = ceil_div(nnz > 0 ? nnz : 1, 1024);  // smallest tile → upper bound
   // tile_row (ntiles+1) + tile_win (2*ntiles) int64, head 16 B/tile, counters, padding
-  return (ntiles + 1) * 8 + ntiles * 16 + ntiles * 16 + ntiles * 16 + 64 + 512;
+  return (ntiles + 1) * 8 + ntiles * 16 + ntiles * 16 + ntiles * 16 + ntiles * 8 * 24 + 64 + 1024;
 }
 
 extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
@@ -471,19 +609,28 @@ extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, 
   cudaStream_t st = (cudaStream_t)stream;
   auto* P = new b2s_spmv_plan();
   P->it = it; P->nrows = nrows; P->ncols = ncols; P->nnz = nnz;
-  P->tile_nnz = default_tile_nnz();
-  P->ntiles = ceil_div(nnz, P->tile_nnz);
-  P->window_tiles = 0; P->head_tiles = 0;
-  // carve workspace (256-byte aligned base assumed from the caller's allocator; align anyway)
-  uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
-  int64_t nt = P->ntiles;
-  P->counters = reinterpret_cast<int64_t*>(base);               base += 64;
-  P->tile_row = reinterpret_cast<int64_t*>(base);               base += (nt + 1) * 8;
-  base = (base + 15) & ~(uintptr_t)15;
-  P->tile_win = reinterpret_cast<int64_t*>(base);               base += nt * 16;
-  P->head = reinterpret_cast<void*>(base);                      base += nt * 16;
-  P->dotp = reinterpret_cast<void*>(base);
-  if (nt > 0) {
+  // Tile size: an explicit B2S_SPMV_TILE_NNZ wins; otherwise plan with 2048-nnz tiles first and,
+  // when the matrix is not window-friendly (x gathers must go to L2), re-plan with 1024-nnz tiles
+  // (the configuration each consumer flavour measured fastest with on B200).
+  const bool forced = getenv("B2S_SPMV_TILE_NNZ") != nullptr;
+  int64_t candidates[2] = {forced ? default_tile_nnz() : 2048, 1024};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    P->tile_nnz = candidates[attempt];
+    P->ntiles = ceil_div(nnz, P->tile_nnz);
+    P->window_tiles = 0; P->head_tiles = 0;
+    // carve workspace (256-byte aligned base assumed from the caller's allocator; align anyway)
+    uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    int64_t nt = P->ntiles;
+    P->counters = reinterpret_cast<int64_t*>(base);               base += 64;
+    P->tile_row = reinterpret_cast<int64_t*>(base);               base += (nt + 1) * 8;
+    base = (base + 15) & ~(uintptr_t)15;
+    P->tile_win = reinterpret_cast<int64_t*>(base);               base += nt * 16;
+    P->head = reinterpret_cast<void*>(base);                      base += nt * 16;
+    P->dotp = reinterpret_cast<void*>(base);                      base += nt * 16;
+    P->sub_head = reinterpret_cast<void*>(base);                  base += nt * 8 * 16;
+    P->sub_head_row = reinterpret_cast<int64_t*>(base);
+    P->empty_rows = 0;
+    if (nt == 0) break;
     cudaError_t e = cudaMemsetAsync(P->counters, 0, 64, st);
     if (e != cudaSuccess) { delete P; set_error("memset failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
     plan_tile_rows_kernel<<<(unsigned)ceil_div(nt + 1, 256), 256, 0, st>>>(nrows, nt, P->tile_nnz, indptr,
@@ -496,13 +643,22 @@ extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, 
       plan_tile_window_kernel<int64_t><<<(unsigned)nt, 128, 0, st>>>(nnz, nt, P->tile_nnz, indptr,
           (const int64_t*)indices, P->tile_row, P->tile_win, P->counters);
     g_launch_count.fetch_add(1);
-    int64_t h[2] = {0, 0};
+    {
+      int64_t blocks = ceil_div(nrows, 256);
+      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      if (blocks < 1) blocks = 1;
+      plan_count_empty_kernel<<<(unsigned)blocks, 256, 0, st>>>(nrows, indptr, P->counters);
+      g_launch_count.fetch_add(1);
+    }
+    int64_t h[3] = {0, 0, 0};
     e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 24, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { delete P; set_error("plan build failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
     P->window_tiles = h[0];
     P->head_tiles = h[1];
+    P->empty_rows = h[2];
+    if (forced || P->window_tiles * 2 >= P->ntiles) break;   // keep this tiling
   }
   *out_plan = P;
   return B2S_OK;
@@ -527,7 +683,7 @@ static int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, 
   B2S_REQUIRE(nrows == 0 || y != nullptr, "y is null");
   B2S_REQUIRE(nrows == 0 || indptr != nullptr, "indptr is null");
   B2S_REQUIRE(nnz == 0 || (indices && data && x), "null matrix/vector arrays");
-  B2S_REQUIRE(variant >= B2S_SPMV_AUTO && variant <= B2S_SPMV_TILE, "bad variant");
+  B2S_REQUIRE(variant >= B2S_SPMV_AUTO && variant <= B2S_SPMV_MERGE, "bad variant");
   cudaStream_t st = (cudaStream_t)stream;
   B2S_DISPATCH_VT(vt, V,
     B2S_DISPATCH_IT(it, I,
@@ -551,6 +707,6 @@ extern "C" int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64
   B2S_REQUIRE(dot_out != nullptr, "dot_out null");
   B2S_REQUIRE(nrows == 0 || w != nullptr, "w null");
   B2S_REQUIRE(plan != nullptr, "fused dot needs a plan");
-  return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_TILE,
+  return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO,
                     dot_out, plan->dotp, w, stream);
 }

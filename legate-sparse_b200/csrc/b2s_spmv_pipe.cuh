@@ -1,0 +1,328 @@
+// b2s_spmv_pipe.cuh — persistent, warp-specialised, TMA-fed CSR SpMV (the default kernel).
+//
+// Included by b2s_spmv.cu.  Same tiling / ownership rules as spmv_tile_kernel (nnz-balanced
+// tiles from the plan; the tile where a row starts owns y[r]; later pieces go to head[t] and
+// are added by spmv_fixup_kernel in tile order), different execution structure:
+//
+//   * persistent CTAs (grid = resident CTAs per SM x 148), tiles handed out round-robin;
+//   * one PRODUCER warp: an elected lane fills a STAGES-deep shared-memory ring with TMA bulk
+//     copies (cp.async.bulk … mbarrier::complete_tx, SASS UBLKCP) of the tile's contiguous
+//     slices: col indices, values, the indptr entries of the tile's rows and — when the plan
+//     says the tile's [min col, max col] image is small (banded / stencil matrices; the
+//     reference's image(crd→x, MIN_MAX), csr.py:591) — the x window itself.  The streams never
+//     touch the LSU/L1TEX path or the register file, so that path is left to the x gathers;
+//   * 8 CONSUMER warps: wait on the stage's "full" mbarrier; a group of 1..32 lanes owns one row
+//     of the tile, walks its (col,val) pairs in shared memory, gathers x (shared-memory window,
+//     else L2 with an evict_last policy), accumulates in registers, shuffle-reduces in a fixed
+//     order and writes y; then each thread arrives on the stage's "empty" mbarrier.  There is
+//     no CTA-wide barrier per tile and no floating-point atomics.
+#pragma once
+
+namespace b2s {
+
+constexpr int kPipeConsumers = 256;
+constexpr int kPipeThreads   = kPipeConsumers + 32;
+constexpr int kPipeWinCap    = 1024;  // x-window capacity per stage (elements)
+
+struct PipeMeta {  // written by the producer before it arms the full barrier
+  int64_t r_begin, r_last;   // rows touched by the tile (r_last may be the sentinel nrows)
+  int64_t ra;                // first indptr entry staged in shared memory
+  int64_t wbase;             // first x element staged (0 if none)
+  int32_t rows_staged;       // 1: indptr entries [ra, …] are in shared memory
+  int32_t win_staged;        // 1: x window is in shared memory
+  int32_t full_tile;         // 1: (col,val) slices are in shared memory
+  int32_t pad;
+};
+
+template <typename V, typename I, int IPT>
+struct PipeLayout {
+  static constexpr int T = kPipeConsumers * IPT;
+  static constexpr int RCAP = T / 4 + 4;            // indptr entries per stage
+  static constexpr size_t vals_off = 0;
+  static constexpr size_t cols_off = vals_off + sizeof(V) * T;
+  static constexpr size_t rptr_off = (cols_off + sizeof(I) * T + 15) / 16 * 16;
+  static constexpr size_t meta_off = rptr_off + 8 * RCAP;
+  static constexpr size_t xwin_off = (meta_off + sizeof(PipeMeta) + 15) / 16 * 16;
+  __host__ __device__ static constexpr size_t stage_bytes(bool window) {
+    return (xwin_off + (window ? sizeof(V) * (kPipeWinCap + 4) : 0) + 127) / 128 * 128;
+  }
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumers) : "memory");
+}
+
+template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool ROWWALK>
+__global__ void __launch_bounds__(kPipeThreads)
+spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
+                 const int64_t* __restrict__ indptr, const I* __restrict__ cols,
+                 const V* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
+                 const int64_t* __restrict__ tile_row, const int64_t* __restrict__ tile_win,
+                 V* __restrict__ head, V* __restrict__ dot_partials, const V* __restrict__ w) {
+  using L = PipeLayout<V, I, IPT>;
+  constexpr int T = L::T;
+  constexpr size_t STAGE = L::stage_bytes(WINDOW);
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + STAGE * STAGES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  __shared__ V wsum[kPipeConsumers / 32];  // DOT only
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kPipeConsumers); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const uint64_t pol_stream = policy_evict_first();
+  const uint64_t pol_keep   = policy_evict_last();
+
+  if (tid >= kPipeConsumers) {
+    // ============================== PRODUCER (one elected lane) ==============================
+    if (tid == kPipeConsumers) {
+      int64_t i = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+        const int s = (int)(i % STAGES);
+        const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        unsigned char* st = smem + STAGE * s;
+        PipeMeta* meta = reinterpret_cast<PipeMeta*>(st + L::meta_off);
+        const int64_t S = t * (int64_t)T;
+        const int64_t E = min(S + (int64_t)T, nnz);
+        const int64_t r_begin = tile_row[t], r_last = tile_row[t + 1];
+        uint32_t tx = 0;
+        // rows: indptr[ra .. e] with ra even (16-byte aligned source)
+        const int64_t e  = min(r_last, nrows - 1) + 1;   // last indptr entry needed
+        const int64_t ra = r_begin & ~(int64_t)1;
+        int64_t n_ent = e - ra + 1;
+        n_ent += (n_ent & 1);
+        const bool rows_ok = (n_ent <= L::RCAP) && (ra + n_ent <= nrows + 1);
+        const bool full = (E - S) == T;
+        int64_t wbase = 0, wcnt = 0;
+        bool win_ok = false;
+        uint32_t win_bytes = 0;
+        if (WINDOW) {
+          wbase = tile_win[2 * t];
+          wcnt  = tile_win[2 * t + 1];
+          if (wcnt > 0 && wcnt <= kPipeWinCap) {
+            constexpr int PER16 = (16 / (int)sizeof(V)) > 0 ? (16 / (int)sizeof(V)) : 1;
+            int64_t want = (wcnt + PER16 - 1) / PER16 * PER16;
+            if (wbase + want <= ncols) { win_ok = true; win_bytes = (uint32_t)(want * sizeof(V)); }
+          }
+        }
+        meta->r_begin = r_begin; meta->r_last = r_last; meta->ra = ra; meta->wbase = wbase;
+        meta->rows_staged = rows_ok; meta->win_staged = win_ok; meta->full_tile = full;
+        if (full) tx += (uint32_t)(T * (sizeof(I) + sizeof(V)));
+        if (rows_ok) tx += (uint32_t)(n_ent * 8);
+        tx += win_bytes;
+        if (tx > 0) {
+          mbar_arrive_expect_tx(&full_bar[s], tx);
+          if (full) {
+            tma_bulk_g2s(st + L::vals_off, vals + S, (uint32_t)(T * sizeof(V)), &full_bar[s], pol_stream);
+            tma_bulk_g2s(st + L::cols_off, cols + S, (uint32_t)(T * sizeof(I)), &full_bar[s], pol_stream);
+          }
+          if (rows_ok) tma_bulk_g2s(st + L::rptr_off, indptr + ra, (uint32_t)(n_ent * 8), &full_bar[s], pol_stream);
+          if (win_ok) tma_bulk_g2s(st + L::xwin_off, x + wbase, win_bytes, &full_bar[s], pol_keep);
+        } else {
+          mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================== CONSUMERS ==================================
+  if constexpr (!ROWWALK) {
+    // "products" consumer (matrices whose x gathers go to L2): every thread issues IPT independent
+    // gathers for IPT staged (col,val) pairs (nnz-balanced, maximal memory-level parallelism),
+    // parks the products in place, and after one named barrier the tile's rows are reduced by
+    // 1..32 lanes per row out of shared memory.
+    int64_t i = 0;
+    V dot_acc = zero_of<V>();
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+      const int s = (int)(i % STAGES);
+      const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+      mbar_wait(&full_bar[s], ph);
+      unsigned char* st = smem + STAGE * s;
+      V* svals = reinterpret_cast<V*>(st + L::vals_off);
+      const I* scols = reinterpret_cast<const I*>(st + L::cols_off);
+      const int64_t* srptr = reinterpret_cast<const int64_t*>(st + L::rptr_off);
+      const V* sxwin = reinterpret_cast<const V*>(st + L::xwin_off);
+      const PipeMeta meta = *reinterpret_cast<const PipeMeta*>(st + L::meta_off);
+      const int64_t S = t * (int64_t)T;
+      const int64_t E = min(S + (int64_t)T, nnz);
+      const bool use_win = WINDOW && meta.win_staged;
+      if (meta.full_tile) {
+#pragma unroll
+        for (int g = 0; g < IPT / 4; ++g) {
+          const int q = (g * kPipeConsumers + tid) * 4;
+          I c[4];
+          V v[4];
+          memcpy(c, scols + q, sizeof(I) * 4);   // LDS.128
+          memcpy(v, svals + q, sizeof(V) * 4);
+          V xv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (use_win) xv[k] = sxwin[(int64_t)c[k] - meta.wbase];
+            else         xv[k] = ld_gather<V>(x + (int64_t)c[k], pol_keep);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = vmul(v[k], xv[k]);
+          memcpy(svals + q, v, sizeof(V) * 4);   // STS.128
+        }
+      } else {
+        for (int64_t p = S + tid; p < E; p += kPipeConsumers) {
+          int64_t c = (int64_t)ld_stream<I>(cols + p, pol_stream);
+          V a = ld_stream<V>(vals + p, pol_stream);
+          V xx = use_win ? sxwin[c - meta.wbase] : ld_gather<V>(x + c, pol_keep);
+          svals[p - S] = vmul(a, xx);
+        }
+      }
+      consumer_bar_sync();
+      const int64_t r_begin = meta.r_begin, r_last = meta.r_last;
+      const int64_t nr = r_last - r_begin + 1;
+      int lanes = 1;
+      while (lanes < 32 && (int64_t)(lanes * 2) * nr <= kPipeConsumers) lanes <<= 1;
+      const int groups = kPipeConsumers / lanes;
+      const int gl = tid & (lanes - 1);
+      for (int64_t base = 0; base < nr; base += groups) {
+        const int64_t r = r_begin + base + tid / lanes;
+        const bool valid = (base + tid / lanes < nr) && (r < nrows);
+        int64_t lo_g = 0, hi_g = 0;
+        if (valid) {
+          if (meta.rows_staged) { lo_g = srptr[r - meta.ra]; hi_g = srptr[r - meta.ra + 1]; }
+          else                  { lo_g = indptr[r];          hi_g = indptr[r + 1]; }
+        }
+        const int lo = (int)(max(lo_g, S) - S), hi = (int)(min(hi_g, E) - S);
+        V s0 = zero_of<V>(), s1 = zero_of<V>();
+        int p = lo + gl;
+        for (; p + 3 * lanes < hi; p += 4 * lanes) {   // 4 loads in flight, 2 accumulators
+          const V a0 = svals[p], a1 = svals[p + lanes], a2 = svals[p + 2 * lanes], a3 = svals[p + 3 * lanes];
+          s0 = vadd(s0, vadd(a0, a2));
+          s1 = vadd(s1, vadd(a1, a3));
+        }
+        for (; p < hi; p += lanes) s0 = vadd(s0, svals[p]);
+        V sum = group_reduce(vadd(s0, s1), lanes);
+        if (valid && gl == 0) {
+          bool wrote = false;
+          if (lo_g < S) { head[t] = sum; wrote = true; }
+          else if (r < r_last || lo_g < E) { y[r] = sum; wrote = true; }
+          if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
+        }
+      }
+      mbar_arrive(&empty_bar[s]);
+    }
+    if (DOT) {
+      V sacc = dot_acc;
+      for (int o = 16; o > 0; o >>= 1) sacc = vadd(sacc, vshfl_xor(sacc, o));
+      if ((tid & 31) == 0) wsum[tid >> 5] = sacc;
+      consumer_bar_sync();
+      if (tid == 0) {
+        V tot = wsum[0];
+        for (int k = 1; k < kPipeConsumers / 32; ++k) tot = vadd(tot, wsum[k]);
+        dot_partials[blockIdx.x] = tot;
+      }
+    }
+    return;
+  }
+  // Row-walk straight out of the staged tile: a group of `lanes` threads owns one row of the
+  // tile, walks its (col,val) pairs in shared memory, gathers x and accumulates in registers.
+  // No product round-trip through shared memory and NO CTA-wide barrier per tile: a thread
+  // that is done with its row(s) releases the stage and moves on to the next tile, so gathers
+  // of different tiles overlap naturally.
+  int64_t i = 0;
+  V dot_acc = zero_of<V>();
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+    const int s = (int)(i % STAGES);
+    const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+    mbar_wait(&full_bar[s], ph);
+    unsigned char* st = smem + STAGE * s;
+    const V* svals = reinterpret_cast<const V*>(st + L::vals_off);
+    const I* scols = reinterpret_cast<const I*>(st + L::cols_off);
+    const int64_t* srptr = reinterpret_cast<const int64_t*>(st + L::rptr_off);
+    const V* sxwin = reinterpret_cast<const V*>(st + L::xwin_off);
+    const PipeMeta meta = *reinterpret_cast<const PipeMeta*>(st + L::meta_off);
+    const int64_t S = t * (int64_t)T;
+    const int64_t E = min(S + (int64_t)T, nnz);
+    const bool use_win = WINDOW && meta.win_staged;
+    const bool staged = meta.full_tile;
+
+    const int64_t r_begin = meta.r_begin, r_last = meta.r_last;
+    const int64_t nr = r_last - r_begin + 1;
+    int lanes = 1;
+    while (lanes < 32 && (int64_t)(lanes * 2) * nr <= kPipeConsumers) lanes <<= 1;
+    const int groups = kPipeConsumers / lanes;
+    const int gl = tid & (lanes - 1);
+    for (int64_t base = 0; base < nr; base += groups) {
+      const int64_t r = r_begin + base + tid / lanes;
+      const bool valid = (base + tid / lanes < nr) && (r < nrows);
+      int64_t lo_g = 0, hi_g = 0;
+      if (valid) {
+        if (meta.rows_staged) { lo_g = srptr[r - meta.ra]; hi_g = srptr[r - meta.ra + 1]; }
+        else                  { lo_g = indptr[r];          hi_g = indptr[r + 1]; }
+      }
+      const int64_t lo = max(lo_g, S), hi = min(hi_g, E);
+      V sum = zero_of<V>();
+      int64_t p = lo + gl;
+      if (staged) {
+        // 4 independent gathers in flight per thread
+        for (; p + 3 * lanes < hi; p += 4 * lanes) {
+          const int q0 = (int)(p - S), q1 = q0 + lanes, q2 = q1 + lanes, q3 = q2 + lanes;
+          const int64_t c0 = (int64_t)scols[q0], c1 = (int64_t)scols[q1], c2 = (int64_t)scols[q2],
+                        c3 = (int64_t)scols[q3];
+          V x0, x1, x2, x3;
+          if (use_win) {
+            x0 = sxwin[c0 - meta.wbase]; x1 = sxwin[c1 - meta.wbase];
+            x2 = sxwin[c2 - meta.wbase]; x3 = sxwin[c3 - meta.wbase];
+          } else {
+            x0 = ld_gather<V>(x + c0, pol_keep); x1 = ld_gather<V>(x + c1, pol_keep);
+            x2 = ld_gather<V>(x + c2, pol_keep); x3 = ld_gather<V>(x + c3, pol_keep);
+          }
+          sum = vfma(svals[q0], x0, sum);
+          sum = vfma(svals[q1], x1, sum);
+          sum = vfma(svals[q2], x2, sum);
+          sum = vfma(svals[q3], x3, sum);
+        }
+        for (; p < hi; p += lanes) {
+          const int q = (int)(p - S);
+          const int64_t c = (int64_t)scols[q];
+          const V xx = use_win ? sxwin[c - meta.wbase] : ld_gather<V>(x + c, pol_keep);
+          sum = vfma(svals[q], xx, sum);
+        }
+      } else {
+        // partial (last) tile: straight from global memory
+        for (; p < hi; p += lanes) {
+          const int64_t c = (int64_t)ld_stream<I>(cols + p, pol_stream);
+          const V a = ld_stream<V>(vals + p, pol_stream);
+          const V xx = use_win ? sxwin[c - meta.wbase] : ld_gather<V>(x + c, pol_keep);
+          sum = vfma(a, xx, sum);
+        }
+      }
+      sum = group_reduce(sum, lanes);
+      if (valid && gl == 0) {
+        bool wrote = false;
+        if (lo_g < S) { head[t] = sum; wrote = true; }                  // continues an earlier row
+        else if (r < r_last || lo_g < E) { y[r] = sum; wrote = true; }  // this tile owns y[r]
+        if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
+      }
+    }
+    mbar_arrive(&empty_bar[s]);  // this thread is done with the stage
+  }
+  if (DOT) {
+    // one deterministic partial per CTA (fixed thread→row mapping, fixed reduction tree)
+    V sacc = dot_acc;
+    for (int o = 16; o > 0; o >>= 1) sacc = vadd(sacc, vshfl_xor(sacc, o));
+    if ((tid & 31) == 0) wsum[tid >> 5] = sacc;
+    consumer_bar_sync();
+    if (tid == 0) {
+      V tot = wsum[0];
+      for (int k = 1; k < kPipeConsumers / 32; ++k) tot = vadd(tot, wsum[k]);
+      dot_partials[blockIdx.x] = tot;
+    }
+  }
+}
+
+}  // namespace b2s

@@ -21,7 +21,7 @@ _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb200sparse.so"
 # enums (include/b200sparse.h)
 B2S_F32, B2S_F64, B2S_C64, B2S_C128 = 0, 1, 2, 3
 B2S_I32, B2S_I64 = 0, 1
-B2S_SPMV_AUTO, B2S_SPMV_ROWVEC, B2S_SPMV_TILE = 0, 1, 2
+B2S_SPMV_AUTO, B2S_SPMV_ROWVEC, B2S_SPMV_TILE, B2S_SPMV_PIPE, B2S_SPMV_MERGE = 0, 1, 2, 3, 4
 
 _lib = None
 _load_error = None

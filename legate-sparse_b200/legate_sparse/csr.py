@@ -566,7 +566,10 @@ class csr_array(CompressedBase):
                 else:
                     assert tuple(out.shape) == (self.shape[0],)
 
-            output = spmv(A, x, out)
+            y_arg = out
+            if out is not None and other_originally_2d:
+                y_arg = out.reshape(-1)  # (n,1) → (n,) view of the caller's buffer
+            output = spmv(A, x, y_arg)
 
             if other_originally_2d and out is None:
                 output = output.reshape((-1, 1))
@@ -696,7 +699,7 @@ def spmv(A: csr_array, x, y=None):
                 y.copy_(y_dev)
             return y
         if isinstance(y, torch.Tensor):
-            y.copy_(y_dev.cpu())
+            y.copy_(y_dev)  # direct D2H (no staging copy when y is pinned)
             return y
         y[...] = to_host(y_dev)
         return y
