@@ -131,6 +131,13 @@ int main(int argc, char** argv) {
   std::string mode = argc > 4 ? argv[4] : "random";
   int64_t m = n;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  if (getenv("SWEEP_L2_PERSIST")) {
+    size_t want = (size_t)atoll(getenv("SWEEP_L2_PERSIST")) << 20;
+    if (want == 0 || want > (size_t)prop.persistingL2CacheMaxSize) want = prop.persistingL2CacheMaxSize;
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    printf("persisting L2 set-aside: %zu MB (max %d MB, window max %d MB)\n", want >> 20,
+           prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
+  }
   printf("device %s, %d SMs, L2 %d MB; n=%lld k=%d mode=%s\n", prop.name, prop.multiProcessorCount,
          prop.l2CacheSize >> 20, (long long)n, k, mode.c_str());
   int64_t* indptr; CK(cudaMalloc(&indptr, (n + 1) * 8));
