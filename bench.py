@@ -357,6 +357,7 @@ def run_b200(args):
         del A
         torch.cuda.empty_cache()
         line["banded"] = banded_leg(args, dist, dev, bounds, rank, peak)
+        line["cg"] = cg_leg(dist, dev, rank)
         if G == 1 and rank == 0:
             line["cusparse"] = cusparse_leg(vals, cols, indptr, x, n, args)
             line["cpu_baseline"] = cpu_baseline_leg(args)
@@ -388,6 +389,39 @@ def full_size_checks(A, x, y_loc, vals, cols, indptr, r0):
     assert lin < 1e-14 and err < 1e-10, (lin, err)
     return {"linearity_relerr": lin, "oracle_rows_checked": int(rows.numel()), "oracle_relerr": err,
             "tolerance": 1e-10}
+
+
+def cg_leg(dist, dev, rank, grid=4096, iters=200):
+    """BASELINE metric, second half: CG iterations/s on the 5-point Laplacian (config 3: 4096^2 grid,
+    fp64), fixed iteration count (no early exit), fused kernels, all ranks."""
+    import torch
+
+    import legate_sparse as sparse
+    import legate_sparse.linalg as linalg
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from side_bench import poisson2d_block
+
+    G = dist.world_size()
+    n = grid * grid
+    bounds = dist.row_block_bounds(n, G)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    data, idx, ptr = poisson2d_block(grid, r0, r1, dev)
+    A = sparse.csr_array.from_row_block(data, idx, ptr, (n, n), row_start=r0, bounds=bounds)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    b = torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    linalg.cg(A, b, rtol=0.0, atol=0.0, maxiter=25)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, it = linalg.cg(A, b, rtol=0.0, atol=0.0, maxiter=iters)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    nnz = A.nnz
+    ref_bytes = nnz * 12 + (n + 1) * 8 + 16 * n + 120 * n
+    return {"workload": f"CG, 5-point Laplacian {grid}x{grid} (n={n}, nnz={nnz}), fp64, identity M, {it} iterations",
+            "iters_per_s": it / dt, "ms_per_iter": dt / it * 1e3,
+            "reference_algorithm_bytes_per_iter": ref_bytes, "fused_bytes_per_iter": ref_bytes - 48 * n,
+            "kernels_per_iter": "cg_pupdate + spmv_pipe(+dot) + fixup + reduce + cg_update (+NCCL all-gather/all-reduce at N>1)"}
 
 
 def banded_leg(args, dist, dev, bounds, rank, peak):

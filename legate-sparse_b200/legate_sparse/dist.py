@@ -42,10 +42,13 @@ def init(backend: str | None = None) -> None:
     use_cuda = torch.cuda.is_available()
     if backend is None:
         backend = "nccl" if use_cuda else "gloo"
-    if use_cuda:
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    td.init_process_group(backend=backend)
+    if use_cuda:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        td.init_process_group(backend=backend, device_id=torch.device("cuda", local))
+    else:
+        td.init_process_group(backend=backend)
 
 
 def shutdown() -> None:

@@ -1,0 +1,78 @@
+"""Worker for tests/test_gpu_dist.py: run under torchrun with N ranks, one GPU each (NCCL)."""
+import os
+import sys
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+for p in (ROOT, os.path.join(ROOT, "legate-sparse_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+import legate_sparse as sparse
+import legate_sparse.linalg as linalg
+from legate_sparse import dist
+from oracle import oracle
+from tests import gen
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+def main():
+    dist.init()
+    G, rank = dist.world_size(), dist.rank()
+    assert G > 1
+    rng = np.random.default_rng(0)  # same on every rank (SPMD: replicated construction)
+    # --- SpMV: replicated result through the public API, ragged blocks (n not divisible by G)
+    n = 10007
+    d, c, p = gen.random_csr_fixed(n, n, 20, seed=3)
+    S = sp.csr_array((d, c, p), shape=(n, n))
+    A = sparse.csr_array(S)
+    x = rng.standard_normal(n)
+    y = A @ x
+    assert relerr(y, S @ x) < 1e-12
+    blk = A._block()
+    assert blk.nrows == dist.row_block_bounds(n, G)[rank + 1] - dist.row_block_bounds(n, G)[rank]
+    yl = A.dot_local(torch.from_numpy(x).cuda())
+    assert relerr(yl.cpu().numpy(), (S @ x)[blk.r0 : blk.r1]) < 1e-12
+    # nnz-balanced partition on a power-law matrix
+    d, c, p = gen.powerlaw_csr(8000, 8000, max_row=4000, seed=7)
+    Sp = sp.csr_array((d, c, p), shape=(8000, 8000))
+    Ap = sparse.csr_array(Sp)
+    Ap.set_row_bounds(dist.nnz_balanced_bounds(p, G))
+    xp = rng.standard_normal(8000)
+    assert relerr(Ap @ xp, Sp @ xp) < 1e-10
+    # --- CG (fused, row-sharded vectors + all-gather of p + all-reduce of the scalars)
+    N = 64
+    P = gen.poisson2d_scipy(N)
+    Ad = sparse.csr_array(P)
+    b = rng.random(N * N)
+    xs, it = linalg.cg(Ad, b, rtol=1e-10)
+    xo, ito = oracle.cg(lambda v: P @ v, b, rtol=1e-10)
+    assert it == ito, (it, ito)
+    assert relerr(xs, xo) < 1e-9
+    # unfused path (replicated vectors)
+    os.environ["LEGATE_SPARSE_CG_UNFUSED"] = "1"
+    xu, itu = linalg.cg(Ad, b, rtol=1e-10)
+    os.environ["LEGATE_SPARSE_CG_UNFUSED"] = "0"
+    assert itu == ito and relerr(xu, xo) < 1e-9
+    # --- SpGEMM: row blocks of A x replicated B, C all-gathered(v)
+    R = gen.rmat_csr(10)
+    C = sparse.csr_array(R) @ sparse.csr_array(R)
+    E = (R @ R).tocsr()
+    E.sort_indices()
+    assert np.array_equal(C.indptr, E.indptr) and np.array_equal(C.indices, E.indices)
+    assert relerr(C.data, E.data) < 1e-12
+    # distributed diagonal
+    assert np.allclose(Ad.diagonal(), P.diagonal())
+    torch.cuda.synchronize()
+    print(f"rank {rank}/{G} OK", flush=True)
+    dist.shutdown()
+
+
+if __name__ == "__main__":
+    main()
