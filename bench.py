@@ -330,7 +330,7 @@ def run_b200(args):
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
            "ms_per_step": e2e_ms / e2e_steps,
            "path": "csr_array.dot(x_pinned_host, out=y_pinned_host): H2D x, SpMV kernels"
-                   + (", NCCL all-gather of y" if G > 1 else "") + ", D2H y; matrix resident in HBM"}
+                   + (", y all-gathered by the kernel's P2P stores" if G > 1 else "") + ", D2H y; matrix resident in HBM"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
@@ -351,7 +351,8 @@ def run_b200(args):
         g_ms, _ = timed_steps(lambda: A.dot(x, out=y_full), args.steps, args.warmup, dist)
         line["gathered"] = {"value": 2.0 * nnz_total / (g_ms / args.steps * 1e-3) / 1e9, "unit": UNIT,
                             "ms_per_step": g_ms / args.steps,
-                            "what": "SpMV + NCCL all-gather of y (replicated result)"}
+                            "what": "SpMV with the all-gather of y fused into the kernel stores (NVLink P2P via symmetric "
+                                    "memory; NCCL all-gather when peer memory is unavailable) + copy into out"}
 
     if not args.no_extras:
         del A

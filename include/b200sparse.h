@@ -97,6 +97,17 @@ int b2s_spmv_csr(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64
                  const void* x, void* y, const b2s_spmv_plan* plan, int variant,
                  b2s_stream_t stream);
 
+/* SpMV fused with the all-gather of y (multi-GPU): besides the local `y` (this rank's
+ * row block) every y[r] is also stored into `y_peers[g][r]`, g < npeers <= 7 — the same row block
+ * inside the replicated result buffers of the OTHER ranks (peer device memory mapped with CUDA
+ * IPC / symmetric memory; pointers already offset to this rank's first row).  The gather rides on
+ * the kernel's own stores over NVLink/NVSwitch instead of a separate ncclAllGather; the caller
+ * brackets the call with a cross-rank barrier.  Needs a plan and 16-byte aligned arrays. */
+int b2s_spmv_csr_bcast(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                       const int64_t* indptr, const void* indices, const void* data,
+                       const void* x, void* y, void* const* y_peers, int npeers,
+                       const b2s_spmv_plan* plan, b2s_stream_t stream);
+
 /* SpMV fused with a dot product:  y = A x;  dot_out[0] = sum_r w[r] * y[r]  (no conjugation).
  * With w = x (+ the row offset of the block) this is the CG pair q=A.matvec(p); pq=p.dot(q)
  * (linalg.py:519-520) in one pass.  `w` has nrows entries, `dot_out` is one device scalar of
@@ -133,6 +144,10 @@ int b2s_cg_update(b2s_dtype vt, int64_t n, void* x, void* r, const void* p, cons
 /* p = r + (rho/rho1) p   (linalg.py:516-518 with z == r); rho1[0]==0 ⇒ p = r */
 int b2s_cg_pupdate(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
                    const void* rho1, b2s_stream_t stream);
+/* same, and the new p block is also stored into the replicated p of every peer rank (fuses the
+ * per-iteration all-gather of p of the row-partitioned CG into the update kernel) */
+int b2s_cg_pupdate_bcast(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
+                         const void* rho1, void* const* p_peers, int npeers, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * CSR x CSR SpGEMM  C = A B.   replaces SpGEMMCSRxCSRxCSRGPU

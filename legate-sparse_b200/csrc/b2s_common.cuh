@@ -293,6 +293,25 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
+// ---------------------------------------------------------------- peer broadcast (NVLink P2P stores)
+// Extra destinations of a result vector: the same row block inside the buffers of the OTHER
+// ranks (pointers already offset to this rank's first row; peer memory mapped through CUDA
+// IPC / symmetric memory).  A kernel that writes y[r] also stores the value to every peer, so
+// the "all-gather" of the row blocks rides on the kernel's own stores over NVLink / NVSwitch.
+constexpr int kMaxPeers = 7;
+template <typename V>
+struct PeerOut {
+  V* p[kMaxPeers];
+  int n;
+};
+template <typename V>
+__device__ __forceinline__ void store_bcast(V* __restrict__ y, const PeerOut<V>& peers, int64_t r, V v) {
+  y[r] = v;
+#pragma unroll
+  for (int g = 0; g < kMaxPeers; ++g)
+    if (g < peers.n) peers.p[g][r] = v;
+}
+
 // ---------------------------------------------------------------- misc
 __host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

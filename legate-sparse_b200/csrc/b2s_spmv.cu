@@ -268,7 +268,8 @@ template <typename V, bool DOT>
 __global__ void spmv_fixup_kernel(int64_t ntiles, int64_t tile_nnz,
                                   const int64_t* __restrict__ indptr,
                                   const int64_t* __restrict__ tile_row,
-                                  const V* __restrict__ head, V* __restrict__ y) {
+                                  const V* __restrict__ head, V* __restrict__ y,
+                                  const PeerOut<V> peers) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < 1 || t >= ntiles) return;
   int64_t r = tile_row[t];
@@ -278,7 +279,7 @@ __global__ void spmv_fixup_kernel(int64_t ntiles, int64_t tile_nnz,
   if (start < S - tile_nnz) return;        // tile t-1 is not the owner → an earlier thread handles r
   V acc = y[r];
   for (int64_t u = t; u < ntiles && tile_row[u] == r; ++u) acc = vadd(acc, head[u]);
-  y[r] = acc;
+  store_bcast(y, peers, r, acc);
 }
 
 // final deterministic reduction of per-tile partials → out[0]
@@ -344,7 +345,7 @@ static int num_sms() {
 template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool ROWWALK>
 static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                            cudaStream_t st) {
+                            const PeerOut<V>& peers, cudaStream_t st) {
   using L = PipeLayout<V, I, IPT>;
   const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
   auto kern = spmv_pipe_kernel<V, I, IPT, STAGES, WINDOW, DOT, ROWWALK>;
@@ -361,7 +362,7 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   *npartials = grid;
   kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals,
                                                    x, y, P->tile_row, P->tile_win,
-                                                   reinterpret_cast<V*>(P->head), dot_partials, w);
+                                                   reinterpret_cast<V*>(P->head), dot_partials, w, peers);
   B2S_CHECK_LAUNCH();
   return B2S_OK;
 }
@@ -405,13 +406,13 @@ static int pipe_stages_default(int ipt) {
 template <typename V, typename I, int IPT, bool DOT>
 static int launch_pipe_ipt(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                            const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                           cudaStream_t st) {
+                           const PeerOut<V>& peers, cudaStream_t st) {
   bool window = (P->window_tiles * 2 >= P->ntiles) && ((uintptr_t)x % 16 == 0) &&
                 getenv("B2S_SPMV_NO_WINDOW") == nullptr;
   // window matrices (banded / stencil): row-walk consumer; others: products consumer.
   // Only STAGES = 2 is instantiated (deeper rings cost CTAs/SM and measured slower).
   const bool rowwalk = window ? (getenv("B2S_SPMV_PRODUCTS") == nullptr) : (getenv("B2S_SPMV_ROWWALK") != nullptr);
-#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, 2, W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, st)
+#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, 2, W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, st)
   if (window) return rowwalk ? B2S_PIPE(true, true) : B2S_PIPE(true, false);
   return rowwalk ? B2S_PIPE(false, true) : B2S_PIPE(false, false);
 #undef B2S_PIPE
@@ -469,7 +470,8 @@ static int launch_tile_ipt(const PlanHeader* P, const int64_t* indptr, const I* 
 
 template <typename V, typename I, bool DOT>
 static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
-                    const V* x, V* y, V* dot_out, V* dot_partials, const V* w, int mode, cudaStream_t st) {
+                    const V* x, V* y, V* dot_out, V* dot_partials, const V* w, int mode,
+                    const PeerOut<V>& peers, cudaStream_t st) {
   int rc;
   int64_t npartials = P->ntiles;
   if (mode == 2) {
@@ -482,8 +484,8 @@ static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, c
     }
     return B2S_OK;   // the merge path has its own fix-up (sub-tile granularity)
   } else if (mode == 1) {
-    if (P->tile_nnz == 1024) rc = launch_pipe_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
-    else                     rc = launch_pipe_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
+    if (P->tile_nnz == 1024) rc = launch_pipe_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, st);
+    else                     rc = launch_pipe_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, st);
   } else
   switch (P->tile_nnz) {
     case 1024: rc = launch_tile_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, st); break;
@@ -495,7 +497,8 @@ static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, c
   if (P->head_tiles > 0) {
     int thr = 256;
     spmv_fixup_kernel<V, DOT><<<(unsigned)ceil_div(P->ntiles, thr), thr, 0, st>>>(
-        P->ntiles, P->tile_nnz, indptr, P->tile_row, reinterpret_cast<const V*>(P->head), y);
+        P->ntiles, P->tile_nnz, indptr, P->tile_row, reinterpret_cast<const V*>(P->head), y,
+        mode == 1 ? peers : PeerOut<V>{});
     B2S_CHECK_LAUNCH();
   }
   if (DOT) {
@@ -539,7 +542,7 @@ __global__ void fill_zero_kernel(int64_t n, V* y) {
 template <typename V, typename I>
 static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* indptr, const I* cols,
                       const V* vals, const V* x, V* y, const PlanHeader* P, int variant, V* dot_out,
-                      V* dot_partials, const V* w, cudaStream_t st) {
+                      V* dot_partials, const V* w, const PeerOut<V>& peers, cudaStream_t st) {
   const bool want_dot = dot_out != nullptr;
   if (nrows == 0) {
     if (want_dot) { fill_zero_kernel<V><<<1, 32, 0, st>>>(1, dot_out); B2S_CHECK_LAUNCH(); }
@@ -572,8 +575,16 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
     }
     int mode = 0;
     if (tma_ok && variant != B2S_SPMV_TILE) mode = (variant == B2S_SPMV_MERGE) ? 2 : 1;
-    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, st);
-    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, st);
+    if (peers.n > 0 && mode != 1) {
+      set_error("peer broadcast needs the pipe kernel (16-byte aligned arrays, 1024/2048-nnz plan)");
+      return B2S_ERR_UNSUPPORTED;
+    }
+    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, peers, st);
+    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, peers, st);
+  }
+  if (peers.n > 0) {
+    set_error("peer broadcast needs a plan");
+    return B2S_ERR_UNSUPPORTED;
   }
   return run_rowvec<V, I>(nrows, nnz, indptr, cols, vals, x, y, st);
 }
@@ -678,17 +689,24 @@ extern "C" int b2s_spmv_plan_info(const b2s_spmv_plan* plan, int64_t* ntiles, in
 static int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
                       const int64_t* indptr, const void* indices, const void* data, const void* x,
                       void* y, const b2s_spmv_plan* plan, int variant, void* dot_out, void* partials,
-                      const void* w, b2s_stream_t stream) {
+                      const void* w, void* const* y_peers, int npeers, b2s_stream_t stream) {
+  B2S_REQUIRE(npeers >= 0 && npeers <= kMaxPeers, "npeers must be in [0,7]");
+  B2S_REQUIRE(npeers == 0 || y_peers != nullptr, "y_peers is null");
   B2S_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative size");
   B2S_REQUIRE(nrows == 0 || y != nullptr, "y is null");
   B2S_REQUIRE(nrows == 0 || indptr != nullptr, "indptr is null");
   B2S_REQUIRE(nnz == 0 || (indices && data && x), "null matrix/vector arrays");
   B2S_REQUIRE(variant >= B2S_SPMV_AUTO && variant <= B2S_SPMV_MERGE, "bad variant");
   cudaStream_t st = (cudaStream_t)stream;
-  B2S_DISPATCH_VT(vt, V,
+  B2S_DISPATCH_VT(vt, V, {
+    PeerOut<V> peers{};
+    peers.n = npeers;
+    for (int g = 0; g < npeers; ++g) peers.p[g] = (V*)y_peers[g];
     B2S_DISPATCH_IT(it, I,
       return spmv_typed<V, I>(nrows, ncols, nnz, indptr, (const I*)indices, (const V*)data,
-                              (const V*)x, (V*)y, plan, variant, (V*)dot_out, (V*)partials, (const V*)w, st)));
+                              (const V*)x, (V*)y, plan, variant, (V*)dot_out, (V*)partials, (const V*)w,
+                              peers, st));
+  });
   return B2S_ERR_ARG;
 }
 
@@ -697,7 +715,16 @@ extern "C" int b2s_spmv_csr(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t n
                             const void* x, void* y, const b2s_spmv_plan* plan, int variant,
                             b2s_stream_t stream) {
   return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, variant, nullptr,
-                    nullptr, nullptr, stream);
+                    nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int b2s_spmv_csr_bcast(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                                  const int64_t* indptr, const void* indices, const void* data,
+                                  const void* x, void* y, void* const* y_peers, int npeers,
+                                  const b2s_spmv_plan* plan, b2s_stream_t stream) {
+  B2S_REQUIRE(plan != nullptr, "broadcast SpMV needs a plan");
+  return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO, nullptr,
+                    nullptr, nullptr, y_peers, npeers, stream);
 }
 
 extern "C" int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
@@ -708,5 +735,5 @@ extern "C" int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64
   B2S_REQUIRE(nrows == 0 || w != nullptr, "w null");
   B2S_REQUIRE(plan != nullptr, "fused dot needs a plan");
   return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO,
-                    dot_out, plan->dotp, w, stream);
+                    dot_out, plan->dotp, w, nullptr, 0, stream);
 }

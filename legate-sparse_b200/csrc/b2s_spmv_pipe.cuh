@@ -61,7 +61,8 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const int64_t* __restrict__ indptr, const I* __restrict__ cols,
                  const V* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
                  const int64_t* __restrict__ tile_row, const int64_t* __restrict__ tile_win,
-                 V* __restrict__ head, V* __restrict__ dot_partials, const V* __restrict__ w) {
+                 V* __restrict__ head, V* __restrict__ dot_partials, const V* __restrict__ w,
+                 const PeerOut<V> peers) {
   using L = PipeLayout<V, I, IPT>;
   constexpr int T = L::T;
   constexpr size_t STAGE = L::stage_bytes(WINDOW);
@@ -209,7 +210,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         if (valid && gl == 0) {
           bool wrote = false;
           if (lo_g < S) { head[t] = sum; wrote = true; }
-          else if (r < r_last || lo_g < E) { y[r] = sum; wrote = true; }
+          else if (r < r_last || lo_g < E) { store_bcast(y, peers, r, sum); wrote = true; }
           if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
         }
       }
@@ -305,7 +306,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
       if (valid && gl == 0) {
         bool wrote = false;
         if (lo_g < S) { head[t] = sum; wrote = true; }                  // continues an earlier row
-        else if (r < r_last || lo_g < E) { y[r] = sum; wrote = true; }  // this tile owns y[r]
+        else if (r < r_last || lo_g < E) { store_bcast(y, peers, r, sum); wrote = true; }  // this tile owns y[r]
         if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
       }
     }

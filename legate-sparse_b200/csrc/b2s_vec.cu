@@ -182,7 +182,7 @@ cg_update_kernel(int64_t n, V* __restrict__ x, V* __restrict__ r, const V* __res
 template <typename V, bool VEC>
 __global__ void __launch_bounds__(kVecThreads)
 cg_pupdate_kernel(int64_t n, V* __restrict__ p, const V* __restrict__ r, const V* __restrict__ rho,
-                  const V* __restrict__ rho1) {
+                  const V* __restrict__ rho1, const PeerOut<V> peers) {
   const V d = rho1[0];
   const bool first = vis_zero(d);
   const V beta = first ? zero_of<V>() : vdiv(rho[0], d);
@@ -201,10 +201,14 @@ cg_pupdate_kernel(int64_t n, V* __restrict__ p, const V* __restrict__ r, const V
         for (int k = 0; k < P::N; ++k) rv.v[k] = vfma(beta, pv.v[k], rv.v[k]);
       }
       pp[i] = rv;
+#pragma unroll
+      for (int g = 0; g < kMaxPeers; ++g)
+        if (g < peers.n) reinterpret_cast<P*>(peers.p[g])[i] = rv;   // 16-byte P2P stores
     }
-    for (int64_t i = np * P::N + i0; i < n; i += stride) p[i] = first ? r[i] : vfma(beta, p[i], r[i]);
+    for (int64_t i = np * P::N + i0; i < n; i += stride)
+      store_bcast(p, peers, i, first ? r[i] : vfma(beta, p[i], r[i]));
   } else {
-    for (int64_t i = i0; i < n; i += stride) p[i] = first ? r[i] : vfma(beta, p[i], r[i]);
+    for (int64_t i = i0; i < n; i += stride) store_bcast(p, peers, i, first ? r[i] : vfma(beta, p[i], r[i]));
   }
 }
 
@@ -302,18 +306,34 @@ extern "C" int b2s_cg_update(b2s_dtype vt, int64_t n, void* x, void* r, const vo
   return B2S_OK;
 }
 
-extern "C" int b2s_cg_pupdate(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
-                              const void* rho1, b2s_stream_t stream) {
+static int cg_pupdate_impl(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
+                           const void* rho1, void* const* p_peers, int npeers, b2s_stream_t stream) {
   B2S_REQUIRE(n >= 0, "negative n");
+  B2S_REQUIRE(npeers >= 0 && npeers <= kMaxPeers, "npeers must be in [0,7]");
   if (n == 0) return B2S_OK;
   B2S_REQUIRE(p && r && rho && rho1, "null pointer");
+  B2S_REQUIRE(npeers == 0 || p_peers, "p_peers is null");
   cudaStream_t st = (cudaStream_t)stream;
   B2S_DISPATCH_VT(vt, V, {
+    PeerOut<V> peers{};
+    peers.n = npeers;
     bool vec = aligned16(p) && aligned16(r);
+    for (int g = 0; g < npeers; ++g) { peers.p[g] = (V*)p_peers[g]; vec = vec && aligned16(p_peers[g]); }
     int64_t grid = vec_grid(ceil_div(n, (int64_t)Pack<V>::N));
-    if (vec) cg_pupdate_kernel<V, true><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1);
-    else     cg_pupdate_kernel<V, false><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1);
+    if (vec) cg_pupdate_kernel<V, true><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1, peers);
+    else     cg_pupdate_kernel<V, false><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1, peers);
     B2S_CHECK_LAUNCH();
   });
   return B2S_OK;
+}
+
+extern "C" int b2s_cg_pupdate(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
+                              const void* rho1, b2s_stream_t stream) {
+  return cg_pupdate_impl(vt, n, p, r, rho, rho1, nullptr, 0, stream);
+}
+
+extern "C" int b2s_cg_pupdate_bcast(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
+                                    const void* rho1, void* const* p_peers, int npeers,
+                                    b2s_stream_t stream) {
+  return cg_pupdate_impl(vt, n, p, r, rho, rho1, p_peers, npeers, stream);
 }

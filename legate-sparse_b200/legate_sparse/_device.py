@@ -183,6 +183,33 @@ def spmv(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan=None, vari
     )
 
 
+def _peer_array(ptrs):
+    arr = (c_void_p * max(len(ptrs), 1))(*[c_void_p(int(q)) for q in ptrs])
+    return arr
+
+
+def spmv_bcast(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y_local, peer_ptrs, plan):
+    """SpMV whose y stores also go to the peers' replicated buffers (fused all-gather)."""
+    arr = _peer_array(peer_ptrs)
+    N.check(
+        N.load().b2s_spmv_csr_bcast(
+            vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y_local),
+            ctypes.cast(arr, c_void_p), len(peer_ptrs), plan.handle, stream_ptr(),
+        ),
+        "spmv_csr_bcast",
+    )
+
+
+def cg_pupdate_bcast(p, r, rho, rho1, peer_ptrs):
+    dt = np_dtype_of(p)
+    arr = _peer_array(peer_ptrs)
+    N.check(
+        N.load().b2s_cg_pupdate_bcast(vt_enum(dt), p.numel(), ptr(p), ptr(r), ptr(rho), ptr(rho1),
+                                      ctypes.cast(arr, c_void_p), len(peer_ptrs), stream_ptr()),
+        "cg_pupdate_bcast",
+    )
+
+
 def spmv_dot(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, w, plan, dot_out):
     N.check(
         N.load().b2s_spmv_csr_dot(

@@ -39,6 +39,7 @@ SIGNATURES = {
     "b2s_spmv_plan_destroy": (None, [_P]),
     "b2s_spmv_plan_info": (c_int, [_P, POINTER(_I64), POINTER(_I64), POINTER(_I64)]),
     "b2s_spmv_csr": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "b2s_spmv_csr_bcast": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     "b2s_spmv_csr_dot": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b2s_axpby": (c_int, [c_int, _I64, _P, _P, _P, _P, c_int, c_int, _P]),
     "b2s_reduce_workspace_bytes": (_I64, []),
@@ -46,6 +47,7 @@ SIGNATURES = {
     "b2s_nrm2": (c_int, [c_int, _I64, _P, _P, _P, _P]),
     "b2s_cg_update": (c_int, [c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b2s_cg_pupdate": (c_int, [c_int, _I64, _P, _P, _P, _P, _P]),
+    "b2s_cg_pupdate_bcast": (c_int, [c_int, _I64, _P, _P, _P, _P, _P, c_int, _P]),
     "b2s_spgemm_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "b2s_spgemm_symbolic": (
         c_int,

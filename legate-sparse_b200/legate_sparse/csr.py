@@ -666,6 +666,11 @@ def _spmv_block(A: csr_array, blk: _RowBlock, x_dev, y_dev):
           x_dev, y_dev, plan=plan, variant=settings.spmv_variant())
 
 
+def _bcast_ok(blk: _RowBlock) -> bool:
+    """the fused SpMV+all-gather needs the TMA pipe kernel: 16-byte aligned arrays"""
+    return all(t.data_ptr() % 16 == 0 for t in (blk.indptr, blk.indices, blk.data))
+
+
 def spmv(A: csr_array, x, y=None):
     """y = A @ x.  Replaces the reference's ``spmv`` task launch (csr.py:562-593): the row
     block of this rank is computed by the sm_100a kernel; with more than one rank the blocks
@@ -687,12 +692,38 @@ def spmv(A: csr_array, x, y=None):
         _spmv_block(A, blk, x_dev, y_dev)
     else:
         bounds = A.row_bounds()
-        if y is not None and _is_dev(y) and y.is_contiguous():
-            y_dev = y
+        from ._device import torch_dtype
+
+        # collective decision (same on every rank): symmetric memory available or not
+        sv = dist.symm_vector(n, torch_dtype(A.dtype), "spmv_y")
+        if sv is not None:
+            # fused SpMV + all-gather: y stores go to every rank's replicated buffer over NVLink
+            from ._device import spmv_bcast, vt_enum
+
+            sv.barrier()   # peers are done reading the previous content
+            local = sv.t[blk.r0 : blk.r1]
+            if blk.nnz > 0 and _bcast_ok(blk):
+                spmv_bcast(vt_enum(A.dtype), blk.itype, blk.nrows, A.shape[1], blk.nnz, blk.indptr,
+                           blk.indices, blk.data, x_dev, local, sv.peer_ptrs(blk.r0), A._plan(blk))
+            else:
+                # rare: empty block or unaligned user slices → local kernel + explicit peer copies
+                _spmv_block(A, blk, x_dev, local)
+                for g in range(G):
+                    if g != dist.rank() and blk.nrows > 0:
+                        sv.h.get_buffer(g, (n,), sv.t.dtype)[blk.r0 : blk.r1].copy_(local)
+            sv.barrier()   # every block has landed everywhere
+            if y is not None and _is_dev(y) and y.is_contiguous():
+                y.copy_(sv.t)
+                y_dev = y
+            else:
+                y_dev = sv.t if y is not None else sv.t.clone()
         else:
-            y_dev = empty(n, A.dtype)
-        _spmv_block(A, blk, x_dev, y_dev[blk.r0 : blk.r1])
-        dist.allgather_into(y_dev, bounds)
+            if y is not None and _is_dev(y) and y.is_contiguous():
+                y_dev = y
+            else:
+                y_dev = empty(n, A.dtype)
+            _spmv_block(A, blk, x_dev, y_dev[blk.r0 : blk.r1])
+            dist.allgather_into(y_dev, bounds)
     if y is not None:
         if _is_dev(y):
             if y_dev is not y:

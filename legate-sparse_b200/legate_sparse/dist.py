@@ -147,3 +147,60 @@ def allgather_varlen(local: torch.Tensor) -> tuple[torch.Tensor, np.ndarray]:
     td.all_gather_into_tensor(recv, send)
     parts = [recv[i * blk : i * blk + int(counts[i])] for i in range(G)]
     return torch.cat(parts), counts
+
+
+# ---------------------------------------------------------------------------- symmetric (peer) memory
+class SymmVector:
+    """A replicated vector whose copy on EVERY rank is mapped into every other rank's address
+    space (torch symmetric memory: CUDA IPC / fabric handles over NVLink).  Kernels that produce
+    a row block store it straight into all copies (b2s_spmv_csr_bcast / b2s_cg_pupdate_bcast):
+    the all-gather is fused into the producing kernel; `barrier()` is the only collective."""
+
+    def __init__(self, n: int, dtype: torch.dtype):
+        import torch.distributed._symmetric_memory as symm
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.t = symm.empty(int(n), dtype=dtype, device=dev)
+        self.h = symm.rendezvous(self.t, td.group.WORLD)
+        self.ptrs = [int(q) for q in self.h.buffer_ptrs]
+        self.itemsize = self.t.element_size()
+
+    def peer_ptrs(self, row_offset: int):
+        me = rank()
+        off = int(row_offset) * self.itemsize
+        return [q + off for g, q in enumerate(self.ptrs) if g != me]
+
+    def barrier(self):
+        self.h.barrier(channel=0)
+
+
+_symm_cache: dict = {}
+_symm_broken = False
+
+
+def symm_vector(n: int, dtype: torch.dtype, tag: str = "y"):
+    """Cached symmetric vector (collective on first use: all ranks must call in the same order).
+    Returns None when peer memory is unavailable → callers fall back to NCCL all-gather."""
+    global _symm_broken
+    if _symm_broken or world_size() == 1 or world_size() > 8 or not torch.cuda.is_available():
+        return None
+    if os.environ.get("LEGATE_SPARSE_NO_SYMM", "0") not in ("0", ""):
+        return None
+    key = (int(n), dtype, tag)
+    v = _symm_cache.get(key)
+    if v is None:
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        try:
+            v = SymmVector(n, dtype)
+        except Exception as e:  # pragma: no cover - depends on the box
+            import warnings
+
+            warnings.warn(f"symmetric memory unavailable ({e}); using NCCL all-gather")
+            ok.zero_()
+            v = None
+        td.all_reduce(ok, op=td.ReduceOp.MIN)   # all ranks agree on the path
+        if int(ok.item()) == 0:
+            _symm_broken = True
+            return None
+        _symm_cache[key] = v
+    return v

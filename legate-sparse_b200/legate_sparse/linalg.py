@@ -392,7 +392,14 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
     cplx = dtype.kind == "c"
 
     # r = b - A x0
-    p_full = D.zeros(n, dtype)
+    pv = dist.symm_vector(n, D.torch_dtype(dtype), "cg_p") if G > 1 else None
+    if pv is not None:
+        p_full = pv.t          # replicated p lives in symmetric memory: peers store into it
+        p_full.zero_()
+        pv.barrier()
+        peer_ptrs = pv.peer_ptrs(r0)
+    else:
+        p_full = D.zeros(n, dtype)
     p_loc = p_full[r0:r1]
     q = D.empty(r1 - r0, dtype)
     x_loc = x[r0:r1] if G > 1 else x
@@ -412,9 +419,15 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
     dist.allreduce_sum_(rho)
     iters = 0
     while iters < maxiter:
-        D.cg_pupdate(p_loc, r, rho, rho1)
-        if G > 1:
-            dist.allgather_into(p_full, bounds)
+        if pv is not None:
+            # no barrier needed before overwriting p_full: the all-reduce of rr at the end of the
+            # previous iteration already orders every rank's SpMV (the reader of p_full) before this point
+            D.cg_pupdate_bcast(p_loc, r, rho, rho1, peer_ptrs)   # p block → every rank (NVLink stores)
+            pv.barrier()                                   # all blocks have landed
+        else:
+            D.cg_pupdate(p_loc, r, rho, rho1)
+            if G > 1:
+                dist.allgather_into(p_full, bounds)
         if plan is not None:
             D.spmv_dot(vt, blk.itype, blk.nrows, A.shape[1], blk.nnz, blk.indptr, blk.indices, blk.data,
                        p_full, q, p_loc, plan, pq)
