@@ -37,7 +37,7 @@ struct PipeMeta {  // written by the producer before it arms the full barrier
 template <typename V, typename I, int IPT>
 struct PipeLayout {
   static constexpr int T = kPipeConsumers * IPT;
-  static constexpr int RCAP = T / 4 + 4;            // indptr entries per stage
+  static constexpr int RCAP = T + 8;                // indptr entries per stage (covers 1 nnz/row)
   static constexpr size_t vals_off = 0;
   static constexpr size_t cols_off = vals_off + sizeof(V) * T;
   static constexpr size_t rptr_off = (cols_off + sizeof(I) * T + 15) / 16 * 16;

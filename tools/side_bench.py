@@ -172,13 +172,94 @@ def run_spgemm(args):
     dist.shutdown()
 
 
+def run_powerlaw(args):
+    """BASELINE config 5: power-law row degrees (Zipf alpha=2 clipped to [1, 10000], one row at
+    10000), n = 8M, uniform columns; SpMV through the public API vs cuSPARSE (torch.sparse)."""
+    dist.init()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = args.pl_rows
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    u = torch.rand(n, device=dev, generator=g, dtype=torch.float64)
+    # inverse-CDF sampling of a discrete power law P(d) ~ d^-2 on [1, 10000]
+    deg = torch.clamp((1.0 / (1.0 - u * (1.0 - 1.0 / 10000.0))).floor().long(), 1, 10000)
+    deg[n // 3] = 10000
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=ptr[1:])
+    nnz = int(ptr[-1].item())
+    cols = torch.randint(0, n, (nnz,), device=dev, generator=g, dtype=torch.int32)
+    vals = torch.rand(nnz, device=dev, generator=g, dtype=torch.float64) - 0.5
+    A = sparse.csr_array((vals, cols, ptr), shape=(n, n))
+    x = torch.rand(n, device=dev, generator=g, dtype=torch.float64)
+    y = A @ x
+    # parity on a row sample (oracle C loop) incl. the longest row
+    from oracle import oracle
+    rows = torch.cat([torch.linspace(0, n - 1, 500, device=dev).long(), torch.tensor([n // 3], device=dev)])
+    xs = x.cpu().numpy()
+    worst = 0.0
+    for r in rows.tolist():
+        lo, hi = int(ptr[r]), int(ptr[r + 1])
+        ref = oracle.spmv(np.array([0, hi - lo]), cols[lo:hi].cpu().numpy(), vals[lo:hi].cpu().numpy(), xs)[0]
+        worst = max(worst, abs(float(y[r]) - ref) / max(abs(ref), 1e-300))
+    out = {"what": f"power-law CSR n={n}, nnz={nnz}, max row 10000 (config 5)", "max_rel_err_vs_oracle_rows": worst}
+    for name, fn in (("b200", lambda: A.dot(x, out=y)),):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        out[name] = {"ms": ms, "gflops": 2.0 * nnz / ms / 1e6, "algorithmic_gbs": (nnz * 12 + n * 24) / ms / 1e6}
+    try:
+        At = torch.sparse_csr_tensor(ptr.to(torch.int32), cols, vals, size=(n, n))  # same index dtype
+        for _ in range(3):
+            At @ x
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            At @ x
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out["cusparse"] = {"ms": ms, "gflops": 2.0 * nnz / ms / 1e6}
+    except Exception as e:
+        out["cusparse"] = {"error": str(e)[:200]}
+    print(json.dumps(out))
+    # cuSPARSE SpGEMM comparison on R-MAT 16 and banded
+    for scale in (16,):
+        data, idx, p2, m = rmat_device(scale, device=dev)
+        B = sparse.csr_array((data, idx, p2), shape=(m, m))
+        dt, C = time_spgemm(B)
+        item = {"what": f"R-MAT {scale} A@A", "b200_ms": dt * 1e3, "nnzC": C.nnz}
+        try:
+            Bt = torch.sparse_csr_tensor(p2, idx.long(), data, size=(m, m))
+            Ct = torch.sparse.mm(Bt, Bt)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                Ct = torch.sparse.mm(Bt, Bt)
+            torch.cuda.synchronize()
+            item["cusparse_ms"] = (time.perf_counter() - t0) / 2 * 1e3
+            item["cusparse_nnzC"] = int(Ct._nnz())
+        except Exception as e:
+            item["cusparse_error"] = str(e)[:200]
+        print(json.dumps(item))
+    dist.shutdown()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["cg", "spgemm"])
+    ap.add_argument("which", choices=["cg", "spgemm", "powerlaw"])
+    ap.add_argument("--pl-rows", type=int, default=8_000_000)
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--scale", type=int, nargs="*", default=[16, 18, 20])
     ap.add_argument("--verify-scale", type=int, default=16)
     ap.add_argument("--banded-n", type=int, default=4_000_000)
     a = ap.parse_args()
-    run_cg(a) if a.which == "cg" else run_spgemm(a)
+    {"cg": run_cg, "spgemm": run_spgemm, "powerlaw": run_powerlaw}[a.which](a)
