@@ -412,7 +412,7 @@ static int launch_pipe_ipt(const PlanHeader* P, const int64_t* indptr, const I* 
   // window matrices (banded / stencil): row-walk consumer; others: products consumer.
   // Only STAGES = 2 is instantiated (deeper rings cost CTAs/SM and measured slower).
   const bool rowwalk = window ? (getenv("B2S_SPMV_PRODUCTS") == nullptr) : (getenv("B2S_SPMV_ROWWALK") != nullptr);
-#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, 2, W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, st)
+#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, (R ? 2 : 3), W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, st)
   if (window) return rowwalk ? B2S_PIPE(true, true) : B2S_PIPE(true, false);
   return rowwalk ? B2S_PIPE(false, true) : B2S_PIPE(false, false);
 #undef B2S_PIPE
