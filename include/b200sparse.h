@@ -77,7 +77,8 @@ typedef struct b2s_spmv_plan b2s_spmv_plan; /* opaque, host object */
  * PIPE   = same TMA ring, consumers walk one row per lane group (kept for A/B measurements)
  * TILE   = one CTA per tile, register-staged 128-bit loads (fallback for unaligned slices)
  * ROWVEC = plan-free 2..32 lanes per row */
-enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2, B2S_SPMV_PIPE = 3, B2S_SPMV_MERGE = 4 };
+enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2, B2S_SPMV_PIPE = 3, B2S_SPMV_MERGE = 4,
+       B2S_SPMV_WPIPE = 5 /* TMA ring + warp-autonomous consumers (no CTA barrier), 1024-nnz plans */ };
 
 /* bytes of device workspace a plan for this matrix needs */
 int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz);

@@ -37,6 +37,7 @@ struct PlanHeader {  // host-side plan object
   void*    sub_head;   // [ntiles*8] * 16 bytes  (merge kernel: per-warp-sub-tile head pieces)
   int64_t* sub_head_row;  // [ntiles*8]          (row*2+first_continuation, or -1)
   int64_t  empty_rows; // number of rows without non-zeros
+  int64_t* sub_row;    // [ntiles*8 + 2] first row of every 128-nnz sub-tile (1024-nnz plans)
   int64_t* counters;   // [4]
 };
 
@@ -330,6 +331,7 @@ spmv_rowvec_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const I* _
 }  // namespace b2s
 #include "b2s_spmv_pipe.cuh"
 #include "b2s_spmv_merge.cuh"
+#include "b2s_spmv_wpipe.cuh"
 namespace b2s {
 
 // ------------------------------------------------------------------ host launchers
@@ -397,6 +399,37 @@ static int launch_merge_inst(const PlanHeader* P, const int64_t* indptr, const I
   return B2S_OK;
 }
 
+template <typename V, typename I, int STAGES, bool DOT>
+static int launch_wpipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
+                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
+                             cudaStream_t st) {
+  using L = PipeLayout<V, I, 4>;
+  const size_t stage = (L::xwin_off + 16 * 8 + 127) / 128 * 128;
+  const size_t smem = stage * STAGES + 16 * STAGES;
+  auto kern = spmv_wpipe_kernel<V, I, STAGES, DOT>;
+  static int blocks_per_sm = -1;  // per instantiation
+  if (blocks_per_sm < 0) {
+    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
+    if (nb < 1) { set_error("spmv_wpipe_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
+    blocks_per_sm = nb;
+  }
+  int64_t grid = (int64_t)blocks_per_sm * num_sms();
+  if (grid > P->ntiles) grid = P->ntiles;
+  *npartials = grid;
+  kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles,
+                                                   P->empty_rows > 0 ? 1 : 0, indptr, cols, vals, x, y,
+                                                   P->sub_row, reinterpret_cast<V*>(P->sub_head),
+                                                   P->sub_head_row, dot_partials, w);
+  B2S_CHECK_LAUNCH();
+  const int64_t nsub = P->ntiles * (kPipeConsumers / 32);
+  spmv_subfixup_kernel<V><<<(unsigned)ceil_div(nsub, 256), 256, 0, st>>>(
+      nsub, P->sub_head_row, reinterpret_cast<const V*>(P->sub_head), y);
+  B2S_CHECK_LAUNCH();
+  return B2S_OK;
+}
+
 static int pipe_stages_default(int ipt) {
   const char* e = getenv("B2S_SPMV_STAGES");
   int s = e ? atoi(e) : (ipt == 4 ? 3 : 2);
@@ -412,7 +445,7 @@ static int launch_pipe_ipt(const PlanHeader* P, const int64_t* indptr, const I* 
   // window matrices (banded / stencil): row-walk consumer; others: products consumer.
   // Only STAGES = 2 is instantiated (deeper rings cost CTAs/SM and measured slower).
   const bool rowwalk = window ? (getenv("B2S_SPMV_PRODUCTS") == nullptr) : (getenv("B2S_SPMV_ROWWALK") != nullptr);
-#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, (R ? 2 : 3), W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, st)
+#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, 2, W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, st)
   if (window) return rowwalk ? B2S_PIPE(true, true) : B2S_PIPE(true, false);
   return rowwalk ? B2S_PIPE(false, true) : B2S_PIPE(false, false);
 #undef B2S_PIPE
@@ -474,6 +507,17 @@ static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, c
                     const PeerOut<V>& peers, cudaStream_t st) {
   int rc;
   int64_t npartials = P->ntiles;
+  if (mode == 3) {
+    const char* e = getenv("B2S_SPMV_STAGES");
+    if (e && atoi(e) == 3) rc = launch_wpipe_inst<V, I, 3, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
+    else                   rc = launch_wpipe_inst<V, I, 2, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
+    if (rc) return rc;
+    if (DOT) {
+      reduce_partials_kernel<V><<<1, 1024, 0, st>>>(npartials, dot_partials, dot_out);
+      B2S_CHECK_LAUNCH();
+    }
+    return B2S_OK;
+  }
   if (mode == 2) {
     if (P->tile_nnz == 1024) rc = launch_merge_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
     else                     rc = launch_merge_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
@@ -555,7 +599,7 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
     return B2S_OK;
   }
   bool use_tile = (P != nullptr) && (variant != B2S_SPMV_ROWVEC);
-  if ((variant == B2S_SPMV_TILE || variant == B2S_SPMV_PIPE || variant == B2S_SPMV_MERGE) && P == nullptr) {
+  if ((variant == B2S_SPMV_TILE || variant == B2S_SPMV_PIPE || variant == B2S_SPMV_MERGE || variant == B2S_SPMV_WPIPE) && P == nullptr) {
     set_error("B2S_SPMV_TILE / B2S_SPMV_PIPE require a plan");
     return B2S_ERR_ARG;
   }
@@ -575,6 +619,13 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
     }
     int mode = 0;
     if (tma_ok && variant != B2S_SPMV_TILE) mode = (variant == B2S_SPMV_MERGE) ? 2 : 1;
+    if (variant == B2S_SPMV_WPIPE) {
+      if (!tma_ok || P->tile_nnz != 1024 || peers.n > 0) {
+        set_error("B2S_SPMV_WPIPE needs aligned arrays, a 1024-nnz plan and no peer broadcast");
+        return B2S_ERR_ARG;
+      }
+      mode = 3;
+    }
     if (peers.n > 0 && mode != 1) {
       set_error("peer broadcast needs the pipe kernel (16-byte aligned arrays, 1024/2048-nnz plan)");
       return B2S_ERR_UNSUPPORTED;
@@ -599,7 +650,7 @@ extern "C" int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz) {
   if (nnz < 0) return -1;
   int64_t ntiles = ceil_div(nnz > 0 ? nnz : 1, 1024);  // smallest tile → upper bound
   // tile_row (ntiles+1) + tile_win (2*ntiles) int64, head 16 B/tile, counters, padding
-  return (ntiles + 1) * 8 + ntiles * 16 + ntiles * 16 + ntiles * 16 + ntiles * 8 * 24 + 64 + 1024;
+  return (ntiles + 1) * 8 + ntiles * 16 + ntiles * 16 + ntiles * 16 + ntiles * 8 * 24 + (ntiles * 8 + 4) * 8 + 64 + 1024;
 }
 
 extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
@@ -639,7 +690,9 @@ extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, 
     P->head = reinterpret_cast<void*>(base);                      base += nt * 16;
     P->dotp = reinterpret_cast<void*>(base);                      base += nt * 16;
     P->sub_head = reinterpret_cast<void*>(base);                  base += nt * 8 * 16;
-    P->sub_head_row = reinterpret_cast<int64_t*>(base);
+    P->sub_head_row = reinterpret_cast<int64_t*>(base);           base += nt * 8 * 8;
+    base = (base + 63) & ~(uintptr_t)63;
+    P->sub_row = reinterpret_cast<int64_t*>(base);
     P->empty_rows = 0;
     if (nt == 0) break;
     cudaError_t e = cudaMemsetAsync(P->counters, 0, 64, st);
@@ -669,6 +722,12 @@ extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, 
     P->window_tiles = h[0];
     P->head_tiles = h[1];
     P->empty_rows = h[2];
+    if (P->tile_nnz == 1024) {
+      // first row of every 128-nnz sub-tile (+2 sentinel entries) for the warp-autonomous kernel
+      const int64_t nsub = nt * 8;
+      plan_tile_rows_kernel<<<(unsigned)ceil_div(nsub + 2, 256), 256, 0, st>>>(nrows, nsub + 1, 128, indptr, P->sub_row);
+      g_launch_count.fetch_add(1);
+    }
     if (forced || P->window_tiles * 2 >= P->ntiles) break;   // keep this tiling
   }
   *out_plan = P;
@@ -696,7 +755,7 @@ static int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, 
   B2S_REQUIRE(nrows == 0 || y != nullptr, "y is null");
   B2S_REQUIRE(nrows == 0 || indptr != nullptr, "indptr is null");
   B2S_REQUIRE(nnz == 0 || (indices && data && x), "null matrix/vector arrays");
-  B2S_REQUIRE(variant >= B2S_SPMV_AUTO && variant <= B2S_SPMV_MERGE, "bad variant");
+  B2S_REQUIRE(variant >= B2S_SPMV_AUTO && variant <= B2S_SPMV_WPIPE, "bad variant");
   cudaStream_t st = (cudaStream_t)stream;
   B2S_DISPATCH_VT(vt, V, {
     PeerOut<V> peers{};

@@ -37,7 +37,7 @@ struct PipeMeta {  // written by the producer before it arms the full barrier
 template <typename V, typename I, int IPT>
 struct PipeLayout {
   static constexpr int T = kPipeConsumers * IPT;
-  static constexpr int RCAP = T + 8;                // indptr entries per stage (covers 1 nnz/row)
+  static constexpr int RCAP = T / 4 + 4;            // indptr entries per stage
   static constexpr size_t vals_off = 0;
   static constexpr size_t cols_off = vals_off + sizeof(V) * T;
   static constexpr size_t rptr_off = (cols_off + sizeof(I) * T + 15) / 16 * 16;
@@ -140,58 +140,38 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     // "products" consumer (matrices whose x gathers go to L2): every thread issues IPT independent
     // gathers for IPT staged (col,val) pairs (nnz-balanced, maximal memory-level parallelism),
     // parks the products in place, and after one named barrier the tile's rows are reduced by
-    // 1..32 lanes per row out of shared memory.  Software-pipelined: the gathers of tile i+1 are
-    // issued BEFORE the barrier + row reduction of tile i, so the L2 gather pipe never drains
-    // while warps wait for each other (needs STAGES >= 3 to keep the TMA producer ahead).
-    V dot_acc = zero_of<V>();
-    V pv[IPT], px[IPT];          // prefetched values / gathered x of the NEXT tile to finish
-    bool pfull = false;
-    auto prefetch = [&](int64_t it, int64_t tt) {
-      const int s2 = (int)(it % STAGES);
-      mbar_wait(&full_bar[s2], (uint32_t)((it / STAGES) & 1));
-      unsigned char* st2 = smem + STAGE * s2;
-      const PipeMeta m2 = *reinterpret_cast<const PipeMeta*>(st2 + L::meta_off);
-      pfull = m2.full_tile;
-      if (pfull) {
-        const V* sv2 = reinterpret_cast<const V*>(st2 + L::vals_off);
-        const I* sc2 = reinterpret_cast<const I*>(st2 + L::cols_off);
-        const V* sx2 = reinterpret_cast<const V*>(st2 + L::xwin_off);
-        const bool uw = WINDOW && m2.win_staged;
-#pragma unroll
-        for (int g = 0; g < IPT / 4; ++g) {
-          const int q = (g * kPipeConsumers + tid) * 4;
-          I c[4];
-          memcpy(c, sc2 + q, sizeof(I) * 4);          // LDS.128
-          memcpy(&pv[g * 4], sv2 + q, sizeof(V) * 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (uw) px[g * 4 + k] = sx2[(int64_t)c[k] - m2.wbase];
-            else    px[g * 4 + k] = ld_gather<V>(x + (int64_t)c[k], pol_keep);
-          }
-        }
-      }
-      (void)tt;
-    };
+    // 1..32 lanes per row out of shared memory.
     int64_t i = 0;
-    int64_t t = blockIdx.x;
-    if (t < ntiles) prefetch(0, t);
-    for (; t < ntiles; t += gridDim.x, ++i) {
+    V dot_acc = zero_of<V>();
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
       const int s = (int)(i % STAGES);
+      const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+      mbar_wait(&full_bar[s], ph);
       unsigned char* st = smem + STAGE * s;
       V* svals = reinterpret_cast<V*>(st + L::vals_off);
+      const I* scols = reinterpret_cast<const I*>(st + L::cols_off);
       const int64_t* srptr = reinterpret_cast<const int64_t*>(st + L::rptr_off);
       const V* sxwin = reinterpret_cast<const V*>(st + L::xwin_off);
       const PipeMeta meta = *reinterpret_cast<const PipeMeta*>(st + L::meta_off);
       const int64_t S = t * (int64_t)T;
       const int64_t E = min(S + (int64_t)T, nnz);
       const bool use_win = WINDOW && meta.win_staged;
-      if (pfull) {
+      if (meta.full_tile) {
 #pragma unroll
         for (int g = 0; g < IPT / 4; ++g) {
           const int q = (g * kPipeConsumers + tid) * 4;
+          I c[4];
           V v[4];
+          memcpy(c, scols + q, sizeof(I) * 4);   // LDS.128
+          memcpy(v, svals + q, sizeof(V) * 4);
+          V xv[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = vmul(pv[g * 4 + k], px[g * 4 + k]);
+          for (int k = 0; k < 4; ++k) {
+            if (use_win) xv[k] = sxwin[(int64_t)c[k] - meta.wbase];
+            else         xv[k] = ld_gather<V>(x + (int64_t)c[k], pol_keep);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = vmul(v[k], xv[k]);
           memcpy(svals + q, v, sizeof(V) * 4);   // STS.128
         }
       } else {
@@ -202,8 +182,6 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           svals[p - S] = vmul(a, xx);
         }
       }
-      // gathers of the next tile go in flight before we wait on anybody
-      if (t + gridDim.x < ntiles) prefetch(i + 1, t + gridDim.x);
       consumer_bar_sync();
       const int64_t r_begin = meta.r_begin, r_last = meta.r_last;
       const int64_t nr = r_last - r_begin + 1;

@@ -21,7 +21,7 @@ class _Settings:
 
     def spmv_variant(self) -> int:
         v = os.environ.get("B2S_SPMV_VARIANT", "auto").lower()
-        return {"auto": 0, "rowvec": 1, "tile": 2, "pipe": 3, "merge": 4}.get(v, 0)
+        return {"auto": 0, "rowvec": 1, "tile": 2, "pipe": 3, "merge": 4, "wpipe": 5}.get(v, 0)
 
 
 settings = _Settings()

@@ -71,6 +71,36 @@ def test_spmv_variants_types(monkeypatch, variant, index64, dtype):
     assert relerr(y, S @ x) < tol
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_spmv_wpipe_variant(monkeypatch, dtype):
+    """warp-autonomous TMA kernel (needs a 1024-nnz plan): irregular rows, empty rows, long rows"""
+    monkeypatch.setenv("B2S_SPMV_VARIANT", "wpipe")
+    monkeypatch.setenv("B2S_SPMV_TILE_NNZ", "1024")
+    rng = np.random.default_rng(12)
+    n, m = 4000, 3500
+    deg = rng.integers(0, 12, size=n)
+    deg[:30] = 0
+    deg[2000:2100] = 0
+    deg[-7:] = 0
+    deg[1234] = 3000
+    deg[77] = 128
+    deg[78] = 1024
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    cols = np.concatenate([np.sort(rng.choice(m, size=k, replace=False)) for k in deg]).astype(np.int64)
+    data = rng.standard_normal(int(indptr[-1])).astype(dtype)
+    x = rng.standard_normal(m).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        data = data + 1j * rng.standard_normal(data.shape[0])
+        x = x + 1j * rng.standard_normal(m)
+    S = sp.csr_array((data, cols, indptr), shape=(n, m))
+    A = sparse.csr_array(S)
+    y = A @ x
+    tol = 1e-10 if np.dtype(dtype) != np.float32 else 3e-5
+    assert relerr(y, S @ x) < tol
+    assert A._block().plan.info()["tile_nnz"] == 1024
+
+
 def _check(A_sp, seed=1, tol=1e-10):
     rng = np.random.default_rng(seed)
     x = rng.standard_normal(A_sp.shape[1])
