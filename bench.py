@@ -224,13 +224,21 @@ def run_reference(args):
     rows = min(args.cpu_sample_rows, n)
     vals, cols, indptr = host_sample(rows, n, k)
     x = np.random.default_rng(1).random(n)
-    threads = oracle.omp_threads()
-    for _ in range(max(args.warmup, 1)):
-        oracle.spmv(indptr, cols, vals, x, omp=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.spmv(indptr, cols, vals, x, omp=True)
-    dt = (time.perf_counter() - t0) / args.steps
+    # all host threads the box offers; hyper-threads often hurt this gather-bound loop, so the
+    # physical-core count is tried as well and the FASTER configuration is the one reported
+    all_threads = oracle.omp_threads()
+    best = None
+    for threads in sorted({all_threads, max(1, all_threads // 2)}, reverse=True):
+        oracle.omp_set_threads(threads)
+        for _ in range(max(args.warmup, 1)):
+            oracle.spmv(indptr, cols, vals, x, omp=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle.spmv(indptr, cols, vals, x, omp=True)
+        dt_try = (time.perf_counter() - t0) / args.steps
+        if best is None or dt_try < best[0]:
+            best = (dt_try, threads)
+    dt, threads = best
     gflops = 2.0 * rows * k / dt / 1e9
     sample = f"first {rows} rows of the {n}x{n} matrix ({rows * k} nnz) per step, int64 column ids"
     line = {

@@ -60,6 +60,10 @@ def omp_threads() -> int:
     return int(_lib().ref_omp_max_threads())
 
 
+def omp_set_threads(n: int) -> None:
+    _lib().ref_omp_set_threads(ctypes.c_int(int(n)))
+
+
 # ------------------------------------------------------------------ C task bodies
 def spmv(indptr, indices, data, x, omp: bool = False):
     """y = A x, reference spmv.cc:36-43 (or spmv_omp.cc:36-44 with omp=True)."""

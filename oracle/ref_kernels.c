@@ -79,6 +79,15 @@ void ref_spmv_omp_f64_i32(int64_t nrows, const int64_t* indptr, const int32_t* c
   }
 }
 
+void ref_omp_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int ref_omp_max_threads(void)
 {
 #ifdef _OPENMP
