@@ -417,13 +417,13 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
     rr = D.zeros(1, dtype)
     D.dot(r, r, out=rho)
     dist.allreduce_sum_(rho)
-    iters = 0
-    while iters < maxiter:
+    def body():
+        """one CG iteration on fixed buffers (capturable in a CUDA graph)"""
         if pv is not None:
             # no barrier needed before overwriting p_full: the all-reduce of rr at the end of the
             # previous iteration already orders every rank's SpMV (the reader of p_full) before this point
             D.cg_pupdate_bcast(p_loc, r, rho, rho1, peer_ptrs)   # p block → every rank (NVLink stores)
-            pv.barrier()                                   # all blocks have landed
+            pv.barrier()                                          # all blocks have landed
         else:
             D.cg_pupdate(p_loc, r, rho, rho1)
             if G > 1:
@@ -437,7 +437,32 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
         dist.allreduce_sum_(pq)
         D.cg_update(x_loc, r, p_loc, q, rho, pq, rr)
         dist.allreduce_sum_(rr)
-        rho1, rho, rr = rho, rr, rho1   # rotate: new rho = rr ; old rho → rho1 ; recycle buffer
+        rho1.copy_(rho)   # old rho → rho1 ; new rho = rr  (z == r)
+        rho.copy_(rr)
+
+    # CUDA graph of the iteration body: removes ~10 launches' worth of host time per iteration
+    # (what bounds multi-GPU / small problems).  LEGATE_SPARSE_CG_GRAPH=0 disables it; collectives
+    # inside the captured body (NCCL all-reduce, symmetric-memory barrier) are captured as well.
+    mode = os.environ.get("LEGATE_SPARSE_CG_GRAPH", "1")
+    graph = None
+    want_graph = callback is None and mode != "0" and (G == 1 or mode == "2")
+    iters = 0
+    while iters < maxiter:
+        if want_graph and graph is None and iters == 1:
+            # iteration 0 ran eagerly (lazy allocations, NCCL warm-up); capture the body now
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+            except Exception as e:  # pragma: no cover - depends on driver / NCCL capture support
+                warnings.warn(f"CUDA graph capture of the CG iteration failed ({e}); running eagerly")
+                graph, want_graph = None, False
+                torch.cuda.synchronize()
+        if graph is not None:
+            graph.replay()
+        else:
+            body()
         iters += 1
         if callback is not None:
             xf = dist.allgather_rows(x_loc, bounds) if G > 1 else x_loc
