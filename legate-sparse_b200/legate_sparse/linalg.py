@@ -441,11 +441,11 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
         rho.copy_(rr)
 
     # CUDA graph of the iteration body: removes ~10 launches' worth of host time per iteration
-    # (what bounds multi-GPU / small problems).  LEGATE_SPARSE_CG_GRAPH=0 disables it; collectives
-    # inside the captured body (NCCL all-reduce, symmetric-memory barrier) are captured as well.
+    # (what bounds multi-GPU / small problems).  LEGATE_SPARSE_CG_GRAPH=0 disables it; the collectives
+    # of the body (NCCL all-reduce, symmetric-memory barrier) are captured with it (measured N=1,2).
     mode = os.environ.get("LEGATE_SPARSE_CG_GRAPH", "1")
     graph = None
-    want_graph = callback is None and mode != "0" and (G == 1 or mode == "2")
+    want_graph = callback is None and mode != "0"
     iters = 0
     while iters < maxiter:
         if want_graph and graph is None and iters == 1:
