@@ -103,7 +103,9 @@ int b2s_spmv_csr(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64
  * inside the replicated result buffers of the OTHER ranks (peer device memory mapped with CUDA
  * IPC / symmetric memory; pointers already offset to this rank's first row).  The gather rides on
  * the kernel's own stores over NVLink/NVSwitch instead of a separate ncclAllGather; the caller
- * brackets the call with a cross-rank barrier.  Needs a plan and 16-byte aligned arrays. */
+ * brackets the call with a cross-rank barrier.  Needs a plan and 16-byte aligned arrays.
+ * npeers == -1: y_peers[0] is an NVSwitch MULTICAST address (NVLS) covering every rank's buffer —
+ * each value is stored once with multimem.st and replicated by the switch. */
 int b2s_spmv_csr_bcast(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
                        const int64_t* indptr, const void* indices, const void* data,
                        const void* x, void* y, void* const* y_peers, int npeers,

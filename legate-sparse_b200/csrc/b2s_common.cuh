@@ -302,14 +302,33 @@ constexpr int kMaxPeers = 7;
 template <typename V>
 struct PeerOut {
   V* p[kMaxPeers];
-  int n;
+  int n;    // number of unicast peers, or -1: p[0] is an NVSwitch MULTICAST address (NVLS) that
+            // maps the same offset of EVERY rank's buffer — one store, the switch replicates it
 };
+// multimem.st: the only legal way to store through a multicast address (PTX ISA, "multimem")
+__device__ __forceinline__ void multimem_st(float* a, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st(double* a, double v) {
+  asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st(c64* a, c64 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(a), "f"(v.re), "f"(v.im) : "memory");
+}
+__device__ __forceinline__ void multimem_st(c128* a, c128 v) {
+  multimem_st(&a->re, v.re);
+  multimem_st(&a->im, v.im);
+}
 template <typename V>
 __device__ __forceinline__ void store_bcast(V* __restrict__ y, const PeerOut<V>& peers, int64_t r, V v) {
   y[r] = v;
+  if (peers.n < 0) {
+    multimem_st(peers.p[0] + r, v);
+  } else {
 #pragma unroll
-  for (int g = 0; g < kMaxPeers; ++g)
-    if (g < peers.n) peers.p[g][r] = v;
+    for (int g = 0; g < kMaxPeers; ++g)
+      if (g < peers.n) peers.p[g][r] = v;
+  }
 }
 
 // ---------------------------------------------------------------- misc

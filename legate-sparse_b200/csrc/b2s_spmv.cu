@@ -620,20 +620,20 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
     int mode = 0;
     if (tma_ok && variant != B2S_SPMV_TILE) mode = (variant == B2S_SPMV_MERGE) ? 2 : 1;
     if (variant == B2S_SPMV_WPIPE) {
-      if (!tma_ok || P->tile_nnz != 1024 || peers.n > 0) {
+      if (!tma_ok || P->tile_nnz != 1024 || peers.n != 0) {
         set_error("B2S_SPMV_WPIPE needs aligned arrays, a 1024-nnz plan and no peer broadcast");
         return B2S_ERR_ARG;
       }
       mode = 3;
     }
-    if (peers.n > 0 && mode != 1) {
+    if (peers.n != 0 && mode != 1) {
       set_error("peer broadcast needs the pipe kernel (16-byte aligned arrays, 1024/2048-nnz plan)");
       return B2S_ERR_UNSUPPORTED;
     }
     if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, peers, st);
     return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, peers, st);
   }
-  if (peers.n > 0) {
+  if (peers.n != 0) {
     set_error("peer broadcast needs a plan");
     return B2S_ERR_UNSUPPORTED;
   }
@@ -749,7 +749,7 @@ static int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, 
                       const int64_t* indptr, const void* indices, const void* data, const void* x,
                       void* y, const b2s_spmv_plan* plan, int variant, void* dot_out, void* partials,
                       const void* w, void* const* y_peers, int npeers, b2s_stream_t stream) {
-  B2S_REQUIRE(npeers >= 0 && npeers <= kMaxPeers, "npeers must be in [0,7]");
+  B2S_REQUIRE(npeers >= -1 && npeers <= kMaxPeers, "npeers must be in [-1,7]");
   B2S_REQUIRE(npeers == 0 || y_peers != nullptr, "y_peers is null");
   B2S_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative size");
   B2S_REQUIRE(nrows == 0 || y != nullptr, "y is null");
@@ -760,7 +760,7 @@ static int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, 
   B2S_DISPATCH_VT(vt, V, {
     PeerOut<V> peers{};
     peers.n = npeers;
-    for (int g = 0; g < npeers; ++g) peers.p[g] = (V*)y_peers[g];
+    for (int g = 0; g < (npeers < 0 ? 1 : npeers); ++g) peers.p[g] = (V*)y_peers[g];
     B2S_DISPATCH_IT(it, I,
       return spmv_typed<V, I>(nrows, ncols, nnz, indptr, (const I*)indices, (const V*)data,
                               (const V*)x, (V*)y, plan, variant, (V*)dot_out, (V*)partials, (const V*)w,

@@ -201,9 +201,14 @@ cg_pupdate_kernel(int64_t n, V* __restrict__ p, const V* __restrict__ r, const V
         for (int k = 0; k < P::N; ++k) rv.v[k] = vfma(beta, pv.v[k], rv.v[k]);
       }
       pp[i] = rv;
+      if (peers.n < 0) {
 #pragma unroll
-      for (int g = 0; g < kMaxPeers; ++g)
-        if (g < peers.n) reinterpret_cast<P*>(peers.p[g])[i] = rv;   // 16-byte P2P stores
+        for (int k = 0; k < P::N; ++k) multimem_st(peers.p[0] + i * P::N + k, rv.v[k]);   // NVLS multicast
+      } else {
+#pragma unroll
+        for (int g = 0; g < kMaxPeers; ++g)
+          if (g < peers.n) reinterpret_cast<P*>(peers.p[g])[i] = rv;   // 16-byte P2P stores
+      }
     }
     for (int64_t i = np * P::N + i0; i < n; i += stride)
       store_bcast(p, peers, i, first ? r[i] : vfma(beta, p[i], r[i]));
@@ -309,7 +314,7 @@ extern "C" int b2s_cg_update(b2s_dtype vt, int64_t n, void* x, void* r, const vo
 static int cg_pupdate_impl(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
                            const void* rho1, void* const* p_peers, int npeers, b2s_stream_t stream) {
   B2S_REQUIRE(n >= 0, "negative n");
-  B2S_REQUIRE(npeers >= 0 && npeers <= kMaxPeers, "npeers must be in [0,7]");
+  B2S_REQUIRE(npeers >= -1 && npeers <= kMaxPeers, "npeers must be in [-1,7]");
   if (n == 0) return B2S_OK;
   B2S_REQUIRE(p && r && rho && rho1, "null pointer");
   B2S_REQUIRE(npeers == 0 || p_peers, "p_peers is null");
@@ -318,7 +323,7 @@ static int cg_pupdate_impl(b2s_dtype vt, int64_t n, void* p, const void* r, cons
     PeerOut<V> peers{};
     peers.n = npeers;
     bool vec = aligned16(p) && aligned16(r);
-    for (int g = 0; g < npeers; ++g) { peers.p[g] = (V*)p_peers[g]; vec = vec && aligned16(p_peers[g]); }
+    for (int g = 0; g < (npeers < 0 ? 1 : npeers); ++g) { peers.p[g] = (V*)p_peers[g]; vec = vec && aligned16(p_peers[g]); }
     int64_t grid = vec_grid(ceil_div(n, (int64_t)Pack<V>::N));
     if (vec) cg_pupdate_kernel<V, true><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1, peers);
     else     cg_pupdate_kernel<V, false><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1, peers);

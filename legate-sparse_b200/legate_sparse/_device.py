@@ -188,13 +188,21 @@ def _peer_array(ptrs):
     return arr
 
 
+def _npeers(peer_ptrs):
+    """peer_ptrs is a list of unicast pointers, or ("mc", ptr) for an NVSwitch multicast address"""
+    if isinstance(peer_ptrs, tuple):
+        return [peer_ptrs[1]], -1
+    return list(peer_ptrs), len(peer_ptrs)
+
+
 def spmv_bcast(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y_local, peer_ptrs, plan):
     """SpMV whose y stores also go to the peers' replicated buffers (fused all-gather)."""
+    peer_ptrs, npeers = _npeers(peer_ptrs)
     arr = _peer_array(peer_ptrs)
     N.check(
         N.load().b2s_spmv_csr_bcast(
             vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y_local),
-            ctypes.cast(arr, c_void_p), len(peer_ptrs), plan.handle, stream_ptr(),
+            ctypes.cast(arr, c_void_p), npeers, plan.handle, stream_ptr(),
         ),
         "spmv_csr_bcast",
     )
@@ -202,10 +210,11 @@ def spmv_bcast(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y_local, pee
 
 def cg_pupdate_bcast(p, r, rho, rho1, peer_ptrs):
     dt = np_dtype_of(p)
+    peer_ptrs, npeers = _npeers(peer_ptrs)
     arr = _peer_array(peer_ptrs)
     N.check(
         N.load().b2s_cg_pupdate_bcast(vt_enum(dt), p.numel(), ptr(p), ptr(r), ptr(rho), ptr(rho1),
-                                      ctypes.cast(arr, c_void_p), len(peer_ptrs), stream_ptr()),
+                                      ctypes.cast(arr, c_void_p), npeers, stream_ptr()),
         "cg_pupdate_bcast",
     )
 

@@ -164,10 +164,20 @@ class SymmVector:
         self.h = symm.rendezvous(self.t, td.group.WORLD)
         self.ptrs = [int(q) for q in self.h.buffer_ptrs]
         self.itemsize = self.t.element_size()
+        self.mc = 0
+        try:  # NVSwitch multicast (NVLS) address of the same buffer on every rank, when supported
+            if os.environ.get("LEGATE_SPARSE_MULTICAST", "0") not in ("0", "") and bool(self.h.has_multicast_support):
+                self.mc = int(self.h.multicast_ptr)
+        except Exception:
+            self.mc = 0
 
     def peer_ptrs(self, row_offset: int):
+        """destinations for a kernel's broadcast stores: ("mc", address) when NVSwitch multicast
+        is available (one store, replicated by the switch), else the unicast peer pointers"""
         me = rank()
         off = int(row_offset) * self.itemsize
+        if self.mc:
+            return ("mc", self.mc + off)
         return [q + off for g, q in enumerate(self.ptrs) if g != me]
 
     def barrier(self):
