@@ -151,6 +151,13 @@ int b2s_cg_pupdate(b2s_dtype vt, int64_t n, void* p, const void* r, const void* 
  * per-iteration all-gather of p of the row-partitioned CG into the update kernel) */
 int b2s_cg_pupdate_bcast(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
                          const void* rho1, void* const* p_peers, int npeers, b2s_stream_t stream);
+/* halo variant: peer g only receives the elements [lo[g], hi[g]) of this block (host arrays,
+ * relative to the block) — the [min col, max col] image of the peer's rows, i.e. the reference's
+ * image(crd→x, MIN_MAX) window (csr.py:591); an empty range (hi<=lo) sends nothing.  For banded /
+ * stencil matrices this turns the all-gather of p into a nearest-neighbour halo exchange. */
+int b2s_cg_pupdate_halo(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
+                        const void* rho1, void* const* p_peers, int npeers, const int64_t* lo,
+                        const int64_t* hi, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * CSR x CSR SpGEMM  C = A B.   replaces SpGEMMCSRxCSRxCSRGPU

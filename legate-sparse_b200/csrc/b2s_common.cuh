@@ -304,7 +304,15 @@ struct PeerOut {
   V* p[kMaxPeers];
   int n;    // number of unicast peers, or -1: p[0] is an NVSwitch MULTICAST address (NVLS) that
             // maps the same offset of EVERY rank's buffer — one store, the switch replicates it
+  // optional per-peer element range [lo, hi) of the local block that the peer actually needs
+  // (halo exchange: the [min col, max col] image of the peer's rows, like the reference's
+  // image(crd→x, MIN_MAX)); hi == 0 means "everything"
+  int64_t lo[kMaxPeers], hi[kMaxPeers];
 };
+template <typename V>
+__device__ __forceinline__ bool peer_wants(const PeerOut<V>& peers, int g, int64_t i) {
+  return peers.hi[g] == 0 || (i >= peers.lo[g] && i < peers.hi[g]);
+}
 // multimem.st: the only legal way to store through a multicast address (PTX ISA, "multimem")
 __device__ __forceinline__ void multimem_st(float* a, float v) {
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
@@ -327,7 +335,7 @@ __device__ __forceinline__ void store_bcast(V* __restrict__ y, const PeerOut<V>&
   } else {
 #pragma unroll
     for (int g = 0; g < kMaxPeers; ++g)
-      if (g < peers.n) peers.p[g][r] = v;
+      if (g < peers.n && peer_wants(peers, g, r)) peers.p[g][r] = v;
   }
 }
 

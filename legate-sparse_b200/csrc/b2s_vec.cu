@@ -207,7 +207,8 @@ cg_pupdate_kernel(int64_t n, V* __restrict__ p, const V* __restrict__ r, const V
       } else {
 #pragma unroll
         for (int g = 0; g < kMaxPeers; ++g)
-          if (g < peers.n) reinterpret_cast<P*>(peers.p[g])[i] = rv;   // 16-byte P2P stores
+          if (g < peers.n && (peers.hi[g] == 0 || ((i + 1) * P::N > peers.lo[g] && i * P::N < peers.hi[g])))
+            reinterpret_cast<P*>(peers.p[g])[i] = rv;   // 16-byte P2P stores (whole pack if it overlaps)
       }
     }
     for (int64_t i = np * P::N + i0; i < n; i += stride)
@@ -312,7 +313,8 @@ extern "C" int b2s_cg_update(b2s_dtype vt, int64_t n, void* x, void* r, const vo
 }
 
 static int cg_pupdate_impl(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
-                           const void* rho1, void* const* p_peers, int npeers, b2s_stream_t stream) {
+                           const void* rho1, void* const* p_peers, int npeers, const int64_t* lo,
+                           const int64_t* hi, b2s_stream_t stream) {
   B2S_REQUIRE(n >= 0, "negative n");
   B2S_REQUIRE(npeers >= -1 && npeers <= kMaxPeers, "npeers must be in [-1,7]");
   if (n == 0) return B2S_OK;
@@ -323,7 +325,11 @@ static int cg_pupdate_impl(b2s_dtype vt, int64_t n, void* p, const void* r, cons
     PeerOut<V> peers{};
     peers.n = npeers;
     bool vec = aligned16(p) && aligned16(r);
-    for (int g = 0; g < (npeers < 0 ? 1 : npeers); ++g) { peers.p[g] = (V*)p_peers[g]; vec = vec && aligned16(p_peers[g]); }
+    for (int g = 0; g < (npeers < 0 ? 1 : npeers); ++g) {
+      peers.p[g] = (V*)p_peers[g];
+      vec = vec && aligned16(p_peers[g]);
+      if (lo && hi && npeers > 0) { peers.lo[g] = lo[g]; peers.hi[g] = hi[g] > lo[g] ? hi[g] : -1; }
+    }
     int64_t grid = vec_grid(ceil_div(n, (int64_t)Pack<V>::N));
     if (vec) cg_pupdate_kernel<V, true><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1, peers);
     else     cg_pupdate_kernel<V, false><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)p, (const V*)r, (const V*)rho, (const V*)rho1, peers);
@@ -334,11 +340,19 @@ static int cg_pupdate_impl(b2s_dtype vt, int64_t n, void* p, const void* r, cons
 
 extern "C" int b2s_cg_pupdate(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
                               const void* rho1, b2s_stream_t stream) {
-  return cg_pupdate_impl(vt, n, p, r, rho, rho1, nullptr, 0, stream);
+  return cg_pupdate_impl(vt, n, p, r, rho, rho1, nullptr, 0, nullptr, nullptr, stream);
 }
 
 extern "C" int b2s_cg_pupdate_bcast(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
                                     const void* rho1, void* const* p_peers, int npeers,
                                     b2s_stream_t stream) {
-  return cg_pupdate_impl(vt, n, p, r, rho, rho1, p_peers, npeers, stream);
+  return cg_pupdate_impl(vt, n, p, r, rho, rho1, p_peers, npeers, nullptr, nullptr, stream);
+}
+
+extern "C" int b2s_cg_pupdate_halo(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
+                                   const void* rho1, void* const* p_peers, int npeers,
+                                   const int64_t* lo, const int64_t* hi, b2s_stream_t stream) {
+  B2S_REQUIRE(npeers >= 0, "halo ranges need unicast peers");
+  B2S_REQUIRE(npeers == 0 || (lo && hi), "null range arrays");
+  return cg_pupdate_impl(vt, n, p, r, rho, rho1, p_peers, npeers, lo, hi, stream);
 }

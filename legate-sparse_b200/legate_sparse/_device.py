@@ -219,6 +219,21 @@ def cg_pupdate_bcast(p, r, rho, rho1, peer_ptrs):
     )
 
 
+def cg_pupdate_halo(p, r, rho, rho1, peer_ptrs, lo, hi):
+    """p update whose result is stored only into the slices the peers need (halo exchange)"""
+    dt = np_dtype_of(p)
+    arr = _peer_array(peer_ptrs)
+    n = max(len(peer_ptrs), 1)
+    lo_a = (c_int64 * n)(*[int(v) for v in lo])
+    hi_a = (c_int64 * n)(*[int(v) for v in hi])
+    N.check(
+        N.load().b2s_cg_pupdate_halo(vt_enum(dt), p.numel(), ptr(p), ptr(r), ptr(rho), ptr(rho1),
+                                     ctypes.cast(arr, c_void_p), len(peer_ptrs), ctypes.cast(lo_a, c_void_p),
+                                     ctypes.cast(hi_a, c_void_p), stream_ptr()),
+        "cg_pupdate_halo",
+    )
+
+
 def spmv_dot(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, w, plan, dot_out):
     N.check(
         N.load().b2s_spmv_csr_dot(

@@ -57,7 +57,7 @@ def _as_host(x, dtype=None, copy=False):
 class _RowBlock:
     """Device-resident rows [r0, r1) of a matrix: rebased indptr, (narrowed) indices, data."""
 
-    __slots__ = ("r0", "r1", "nnz", "indptr", "indices", "data", "itype", "plan")
+    __slots__ = ("r0", "r1", "nnz", "indptr", "indices", "data", "itype", "plan", "_colrange")
 
     def __init__(self, r0, r1, indptr, indices, data):
         self.r0, self.r1 = int(r0), int(r1)
@@ -65,10 +65,22 @@ class _RowBlock:
         self.nnz = int(data.numel())
         self.itype = N.B2S_I32 if indices.dtype == torch.int32 else N.B2S_I64
         self.plan = None
+        self._colrange = None
 
     @property
     def nrows(self):
         return self.r1 - self.r0
+
+    def colrange(self):
+        """[min col, max col] touched by this row block = the x window the block needs
+        (the reference's image(crd→x, MIN_MAX), csr.py:591); (1, 0) for an empty block."""
+        if self._colrange is None:
+            if self.nnz == 0:
+                self._colrange = (1, 0)
+            else:
+                mn, mx = torch.aminmax(self.indices)
+                self._colrange = (int(mn.item()), int(mx.item()))
+        return self._colrange
 
 
 class csr_array(CompressedBase):

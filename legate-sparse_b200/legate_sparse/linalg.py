@@ -398,6 +398,26 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
         p_full.zero_()
         pv.barrier()
         peer_ptrs = pv.peer_ptrs(r0)
+        # halo exchange: peer g only needs the part of my p block inside the [min col, max col]
+        # image of ITS rows (banded / stencil matrices: a few boundary rows instead of the block)
+        halo = None
+        if not isinstance(peer_ptrs, tuple) and os.environ.get("LEGATE_SPARSE_NO_HALO", "0") in ("0", ""):
+            cr = torch.tensor(list(blk.colrange()), dtype=torch.int64, device=p_full.device)
+            allcr = torch.empty(2 * G, dtype=torch.int64, device=p_full.device)
+            torch.distributed.all_gather_into_tensor(allcr, cr)
+            allcr = allcr.cpu().numpy().reshape(G, 2)
+            lo, hi = [], []
+            for g in range(G):
+                if g == dist.rank():
+                    continue
+                a, b = max(int(allcr[g, 0]), r0), min(int(allcr[g, 1]) + 1, r1)
+                lo.append(max(a - r0, 0))
+                hi.append(max(b - r0, 0) if b > a else 0)
+                if b <= a:
+                    lo[-1], hi[-1] = 1, 0          # empty: this peer never reads my block
+            sent = sum(max(h - l, 0) for l, h in zip(lo, hi))
+            if sent < (G - 1) * (r1 - r0):          # otherwise every peer needs everything
+                halo = (lo, hi)
     else:
         p_full = D.zeros(n, dtype)
     p_loc = p_full[r0:r1]
@@ -422,7 +442,10 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
         if pv is not None:
             # no barrier needed before overwriting p_full: the all-reduce of rr at the end of the
             # previous iteration already orders every rank's SpMV (the reader of p_full) before this point
-            D.cg_pupdate_bcast(p_loc, r, rho, rho1, peer_ptrs)   # p block → every rank (NVLink stores)
+            if halo is not None:
+                D.cg_pupdate_halo(p_loc, r, rho, rho1, peer_ptrs, halo[0], halo[1])   # boundary slices only
+            else:
+                D.cg_pupdate_bcast(p_loc, r, rho, rho1, peer_ptrs)   # p block → every rank (NVLink stores)
             pv.barrier()                                          # all blocks have landed
         else:
             D.cg_pupdate(p_loc, r, rho, rho1)
