@@ -60,6 +60,21 @@ def main():
     xu, itu = linalg.cg(Ad, b, rtol=1e-10)
     os.environ["LEGATE_SPARSE_CG_UNFUSED"] = "0"
     assert itu == ito and relerr(xu, xo) < 1e-9
+    # halo exchange with a WIDE band (image reaches several hundred rows into the neighbour block)
+    # and ragged nnz-balanced blocks
+    nb = 3001
+    half = 350
+    W = sp.diags([np.full(nb - abs(o), -1.0 / (1 + abs(o))) for o in range(-half, half + 1, 7)],
+                 list(range(-half, half + 1, 7)), format="csr", dtype=np.float64)
+    W = (W + sp.eye(nb, format="csr") * (abs(W).sum(axis=1).max() + 1.0)).tocsr()
+    Aw = sparse.csr_array(W)
+    Aw.set_row_bounds(dist.nnz_balanced_bounds(W.indptr.astype(np.int64), G))
+    bw = rng.random(nb)
+    xw, itw = linalg.cg(Aw, bw, rtol=1e-11)
+    xow, itow = oracle.cg(lambda v: W @ v, bw, rtol=1e-11)
+    assert itw == itow, (itw, itow)
+    assert relerr(xw, xow) < 1e-10
+    assert relerr(W @ xw, bw) < 1e-10
     # --- SpGEMM: row blocks of A x replicated B, C all-gathered(v)
     R = gen.rmat_csr(10)
     C = sparse.csr_array(R) @ sparse.csr_array(R)

@@ -146,6 +146,21 @@ def test_cg_device_tensors_and_x0_and_preconditioner():
     assert np.linalg.norm(x3 - xo) / np.linalg.norm(xo) < 1e-9
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-4), (np.complex128, 1e-9)])
+def test_cg_other_dtypes(dtype, tol):
+    """f32 and c128 instantiations of the fused CG kernels (the reference's dtype set)."""
+    N = 48
+    S = gen.poisson2d_scipy(N).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        S = (S + 1j * 0.0 * S).tocsr()          # real SPD stored as complex (dot is unconjugated)
+    A = csr_array(S)
+    assert A.dtype == np.dtype(dtype)
+    b = np.random.default_rng(8).random(N * N).astype(dtype)
+    x, it = linalg.cg(A, b, rtol=1e-5 if dtype == np.float32 else 1e-10)
+    assert x.dtype == np.dtype(dtype) and it > 0
+    assert np.linalg.norm(S @ x - b) / np.linalg.norm(b) < tol
+
+
 def test_gmres_solve_reference_system():
     Ad, x = _spd()
     A = csr_array(Ad)

@@ -140,6 +140,19 @@ def run_spgemm(args):
         res.append({"what": f"banded {n}x{n}, {k}/row: A@A", "ms": dt * 1e3, "nnzA": A.nnz, "nnzC": C.nnz,
                     "products": prod, "gflops": 2.0 * prod / dt / 1e9,
                     "lower_bound_gbs": ((2 * A.nnz + C.nnz) * 12 + 3 * (n + 1) * 8) / dt / 1e9})
+        try:   # vendor comparison (bench-only): cuSPARSE SpGEMM through torch.sparse.mm
+            blk = A._block()
+            At = torch.sparse_csr_tensor(blk.indptr.to(torch.int32), blk.indices, blk.data, size=(n, n))
+            Ct = torch.sparse.mm(At, At)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                Ct = torch.sparse.mm(At, At)
+            torch.cuda.synchronize()
+            res[-1]["cusparse_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+            del At, Ct
+        except Exception as e:
+            res[-1]["cusparse_error"] = str(e)[:160]
         del A, C
     for scale in args.scale:
         data, idx, ptr, n = rmat_device(scale, device=dev)
