@@ -6,8 +6,11 @@
 //
 // Rows of A are binned by their work (upper bound = intermediate products for the symbolic
 // pass, exact nnz(C_i) for the numeric pass):
-//   class 1  <=   64 entries : one WARP per row, 128-slot hash table in shared memory
-//   class 2  <=  512 entries : one 128-thread CTA per row, 1024-slot table
+//   class 1  <=  128 entries : one WARP per row, 256-slot hash table in shared memory; the lanes
+//                              are split into groups of 8/16/32 so that several short B rows are
+//                              expanded at once; the finished row is compacted and only
+//                              pow2ceil(nnz) entries are sorted (in registers when <= 32)
+//   class 2  <= 1024 entries : one 128-thread CTA per row, 2048-slot table
 //   class 3  <= 4096 entries : one 512-thread CTA per row, 8192-slot table
 //   class 4  larger          : persistent 1024-thread CTAs, each owning a DENSE accumulator
 //                              (ncolsB values + a bitmap) in HBM — Gustavson's dense workspace,
@@ -20,8 +23,8 @@
 
 namespace b2s {
 
-constexpr int kT1 = 128, kT2 = 1024, kT3 = 8192;
-constexpr int64_t kCap1 = 64, kCap2 = 512, kCap3 = 4096;
+constexpr int kT1 = 256, kT2 = 2048, kT3 = 8192;
+constexpr int64_t kCap1 = 128, kCap2 = 1024, kCap3 = 4096;
 constexpr int kScanBlock = 1024;
 
 // ------------------------------------------------------------------ atomics on value types
@@ -48,7 +51,8 @@ template <> struct key_traits<int64_t> {
 
 template <int TABLE, typename I>
 __device__ __forceinline__ uint32_t hash_slot(I key) {
-  constexpr int LOG = (TABLE == 128) ? 7 : (TABLE == 1024) ? 10 : 13;
+  constexpr int LOG = (TABLE == 256) ? 8 : (TABLE == 2048) ? 11 : 13;
+  static_assert(TABLE == 256 || TABLE == 2048 || TABLE == 8192, "unsupported hash table size");
   uint32_t k = (uint32_t)key ^ (uint32_t)((uint64_t)key >> 32);
   return (k * 0x9E3779B1u) >> (32 - LOG);
 }
@@ -218,7 +222,7 @@ template <typename I, int TABLE, int THREADS, bool WARP_PER_ROW>
 __global__ void __launch_bounds__(THREADS)
 sym_hash_kernel(int64_t nlist, const int32_t* __restrict__ list, const int64_t* __restrict__ a_ptr,
                 const I* __restrict__ a_col, const int64_t* __restrict__ b_ptr,
-                const I* __restrict__ b_col, int64_t* __restrict__ row_nnz) {
+                const I* __restrict__ b_col, int64_t* __restrict__ row_nnz, int gs) {
   constexpr int GROUPS = WARP_PER_ROW ? THREADS / 32 : 1;
   constexpr int GT = WARP_PER_ROW ? 32 : THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -235,12 +239,14 @@ sym_hash_kernel(int64_t nlist, const int32_t* __restrict__ list, const int64_t* 
   int64_t row = -1;
   if (li < nlist) {
     row = list[li];
-    const int lane = threadIdx.x & 31;
-    const int sub = WARP_PER_ROW ? 0 : (threadIdx.x >> 5);
-    const int nsub = WARP_PER_ROW ? 1 : THREADS / 32;
+    // warp rows: `gs` lanes per A entry (32/gs entries in flight); CTA rows: one warp per A entry
+    const int lane = WARP_PER_ROW ? (threadIdx.x & (gs - 1)) : (threadIdx.x & 31);
+    const int step = WARP_PER_ROW ? gs : 32;
+    const int sub = WARP_PER_ROW ? ((threadIdx.x & 31) / gs) : (threadIdx.x >> 5);
+    const int nsub = WARP_PER_ROW ? 32 / gs : THREADS / 32;
     for (int64_t pa = a_ptr[row] + sub; pa < a_ptr[row + 1]; pa += nsub) {
       int64_t k = (int64_t)a_col[pa];
-      for (int64_t pb = b_ptr[k] + lane; pb < b_ptr[k + 1]; pb += 32) {
+      for (int64_t pb = b_ptr[k] + lane; pb < b_ptr[k + 1]; pb += step) {
         uint32_t s;
         if (hash_insert<TABLE, I>(mykeys, b_col[pb], s)) ++local;
       }
@@ -284,7 +290,7 @@ num_hash_kernel(int64_t nlist, const int32_t* __restrict__ list, const int64_t* 
                 const I* __restrict__ a_col, const V* __restrict__ a_val,
                 const int64_t* __restrict__ b_ptr, const I* __restrict__ b_col,
                 const V* __restrict__ b_val, const int64_t* __restrict__ c_ptr, I* __restrict__ c_col,
-                V* __restrict__ c_val) {
+                V* __restrict__ c_val, int gs) {
   constexpr int GROUPS = WARP_PER_ROW ? THREADS / 32 : 1;
   constexpr int GT = WARP_PER_ROW ? 32 : THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -300,13 +306,14 @@ num_hash_kernel(int64_t nlist, const int32_t* __restrict__ list, const int64_t* 
   int64_t row = -1;
   if (li < nlist) {
     row = list[li];
-    const int lane = threadIdx.x & 31;
-    const int sub = WARP_PER_ROW ? 0 : (threadIdx.x >> 5);
-    const int nsub = WARP_PER_ROW ? 1 : THREADS / 32;
+    const int lane = WARP_PER_ROW ? (threadIdx.x & (gs - 1)) : (threadIdx.x & 31);
+    const int step = WARP_PER_ROW ? gs : 32;
+    const int sub = WARP_PER_ROW ? ((threadIdx.x & 31) / gs) : (threadIdx.x >> 5);
+    const int nsub = WARP_PER_ROW ? 32 / gs : THREADS / 32;
     for (int64_t pa = a_ptr[row] + sub; pa < a_ptr[row + 1]; pa += nsub) {
       int64_t k = (int64_t)a_col[pa];
       V av = a_val[pa];
-      for (int64_t pb = b_ptr[k] + lane; pb < b_ptr[k + 1]; pb += 32) {
+      for (int64_t pb = b_ptr[k] + lane; pb < b_ptr[k + 1]; pb += step) {
         uint32_t s;
         hash_insert<TABLE, I>(keys, b_col[pb], s);
         vatomic_add(&vals[s], vmul(av, b_val[pb]));
@@ -314,11 +321,77 @@ num_hash_kernel(int64_t nlist, const int32_t* __restrict__ list, const int64_t* 
     }
   }
   if (WARP_PER_ROW) __syncwarp(); else __syncthreads();
-  bitonic_sort_kv<I, V, TABLE, GT, WARP_PER_ROW>(keys, vals, gt);
-  if (row >= 0) {
-    int64_t o = c_ptr[row];
-    int64_t n = c_ptr[row + 1] - o;
-    for (int64_t i = gt; i < n; i += GT) { c_col[o + i] = keys[i]; c_val[o + i] = vals[i]; }
+  if constexpr (WARP_PER_ROW) {
+    // ---- in-place compaction of the occupied slots to the front (32 slots per step) ----
+    using U = typename key_traits<I>::U;
+    const int lane = threadIdx.x & 31;
+    int n = 0;
+#pragma unroll 1
+    for (int b0 = 0; b0 < TABLE; b0 += 32) {
+      const I kk = keys[b0 + lane];
+      const V vv = vals[b0 + lane];
+      const bool valid = kk != key_traits<I>::EMPTY;
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      __syncwarp();                      // everybody has read its slot before anyone overwrites
+      if (valid) {
+        const int pos = n + __popc(m & ((1u << lane) - 1));
+        keys[pos] = kk;
+        vals[pos] = vv;
+      }
+      n += __popc(m);
+      __syncwarp();
+    }
+    if (row >= 0) {
+      const int64_t o = c_ptr[row];
+      if (n <= 32) {
+        // ---- register bitonic sort of <= 32 (key,val) pairs by shuffles ----
+        U key = lane < n ? (U)keys[lane] : ~(U)0;
+        V val = lane < n ? vals[lane] : zero_of<V>();
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            const U okey = __shfl_xor_sync(0xffffffffu, key, j);
+            const V oval = vshfl_xor(val, j);
+            const bool up = ((lane & k) == 0);
+            const bool lower = ((lane & j) == 0);
+            const bool take_other = (lower == up) ? (okey < key) : (okey > key);
+            if (take_other) { key = okey; val = oval; }
+          }
+        }
+        if (lane < n) { c_col[o + lane] = (I)key; c_val[o + lane] = val; }
+      } else {
+        // ---- shared-memory bitonic over pow2ceil(n) entries ----
+        int mpow = 64;
+        while (mpow < n) mpow <<= 1;
+        for (int i = n + lane; i < mpow; i += 32) { keys[i] = key_traits<I>::EMPTY; vals[i] = zero_of<V>(); }
+        __syncwarp();
+        for (int k = 2; k <= mpow; k <<= 1) {
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < mpow; i += 32) {
+              const int ixj = i ^ j;
+              if (ixj > i) {
+                const U a = (U)keys[i], b = (U)keys[ixj];
+                const bool up = ((i & k) == 0);
+                if ((a > b) == up) {
+                  keys[i] = (I)b; keys[ixj] = (I)a;
+                  const V t = vals[i]; vals[i] = vals[ixj]; vals[ixj] = t;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        for (int i = lane; i < n; i += 32) { c_col[o + i] = keys[i]; c_val[o + i] = vals[i]; }
+      }
+    }
+  } else {
+    bitonic_sort_kv<I, V, TABLE, GT, WARP_PER_ROW>(keys, vals, gt);
+    if (row >= 0) {
+      int64_t o = c_ptr[row];
+      int64_t n = c_ptr[row + 1] - o;
+      for (int64_t i = gt; i < n; i += GT) { c_col[o + i] = keys[i]; c_val[o + i] = vals[i]; }
+    }
   }
 }
 
@@ -426,6 +499,12 @@ dense_row_kernel(int64_t nlist, const int32_t* __restrict__ list, int64_t ncolsB
 }
 
 // ------------------------------------------------------------------ host side
+// lanes per A entry in the warp-per-row kernels: short B rows → several B rows expanded at once
+static int lane_group_size(int64_t nnzB, int64_t nrowsB) {
+  double avg = nrowsB > 0 ? (double)nnzB / (double)nrowsB : 32.0;
+  return avg <= 12.0 ? 8 : (avg <= 24.0 ? 16 : 32);
+}
+
 static int64_t ws_bytes(int64_t nrows) {
   return 256 + 16 * 8 + nrows * 8 + 4 * nrows * 4 + 16 + (ceil_div(nrows > 0 ? nrows : 1, kScanBlock) + 1) * 8 + 256;
 }
@@ -481,7 +560,7 @@ static void free_dense(DenseScratch* D, cudaStream_t st) {
 
 template <typename I, int TABLE, int THREADS, bool WARP>
 static int launch_sym_hash(int64_t n, const int32_t* list, const int64_t* a_ptr, const I* a_col,
-                           const int64_t* b_ptr, const I* b_col, int64_t* row_nnz, cudaStream_t st) {
+                           const int64_t* b_ptr, const I* b_col, int64_t* row_nnz, int gs, cudaStream_t st) {
   constexpr int GROUPS = WARP ? THREADS / 32 : 1;
   size_t smem = sizeof(I) * (size_t)GROUPS * TABLE;
   auto kern = sym_hash_kernel<I, TABLE, THREADS, WARP>;
@@ -490,7 +569,7 @@ static int launch_sym_hash(int64_t n, const int32_t* list, const int64_t* a_ptr,
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  kern<<<(unsigned)ceil_div(n, GROUPS), THREADS, smem, st>>>(n, list, a_ptr, a_col, b_ptr, b_col, row_nnz);
+  kern<<<(unsigned)ceil_div(n, GROUPS), THREADS, smem, st>>>(n, list, a_ptr, a_col, b_ptr, b_col, row_nnz, gs);
   B2S_CHECK_LAUNCH();
   return B2S_OK;
 }
@@ -498,7 +577,7 @@ static int launch_sym_hash(int64_t n, const int32_t* list, const int64_t* a_ptr,
 template <typename I>
 static int symbolic_typed(int64_t nrowsA, int64_t ncolsB, const int64_t* a_ptr, const I* a_col,
                           const int64_t* b_ptr, const I* b_col, int64_t* c_ptr, void* workspace,
-                          int64_t* out_nnzC, int64_t* out_products, cudaStream_t st) {
+                          int64_t* out_nnzC, int64_t* out_products, int gs, cudaStream_t st) {
   SpgemmWs W = carve_ws(workspace, nrowsA);
   B2S_CUDA_TRY(cudaMemsetAsync(W.counters, 0, 16 * 8, st));
   if (nrowsA == 0) {
@@ -521,15 +600,15 @@ static int symbolic_typed(int64_t nrowsA, int64_t ncolsB, const int64_t* a_ptr, 
   B2S_CUDA_TRY(cudaMemsetAsync(c_ptr, 0, (size_t)(nrowsA + 1) * 8, st));
   // NB: kernels index row_nnz[row]
   if (cc.n[1] > 0) {
-    rc = launch_sym_hash<I, kT1, 256, true>(cc.n[1], W.list[1], a_ptr, a_col, b_ptr, b_col, row_nnz, st);
+    rc = launch_sym_hash<I, kT1, 256, true>(cc.n[1], W.list[1], a_ptr, a_col, b_ptr, b_col, row_nnz, gs, st);
     if (rc) return rc;
   }
   if (cc.n[2] > 0) {
-    rc = launch_sym_hash<I, kT2, 128, false>(cc.n[2], W.list[2], a_ptr, a_col, b_ptr, b_col, row_nnz, st);
+    rc = launch_sym_hash<I, kT2, 128, false>(cc.n[2], W.list[2], a_ptr, a_col, b_ptr, b_col, row_nnz, gs, st);
     if (rc) return rc;
   }
   if (cc.n[3] > 0) {
-    rc = launch_sym_hash<I, kT3, 512, false>(cc.n[3], W.list[3], a_ptr, a_col, b_ptr, b_col, row_nnz, st);
+    rc = launch_sym_hash<I, kT3, 512, false>(cc.n[3], W.list[3], a_ptr, a_col, b_ptr, b_col, row_nnz, gs, st);
     if (rc) return rc;
   }
   DenseScratch D;
@@ -563,7 +642,7 @@ static int symbolic_typed(int64_t nrowsA, int64_t ncolsB, const int64_t* a_ptr, 
 template <typename V, typename I, int TABLE, int THREADS, bool WARP>
 static int launch_num_hash(int64_t n, const int32_t* list, const int64_t* a_ptr, const I* a_col,
                            const V* a_val, const int64_t* b_ptr, const I* b_col, const V* b_val,
-                           const int64_t* c_ptr, I* c_col, V* c_val, cudaStream_t st) {
+                           const int64_t* c_ptr, I* c_col, V* c_val, int gs, cudaStream_t st) {
   constexpr int GROUPS = WARP ? THREADS / 32 : 1;
   size_t smem = (sizeof(V) + sizeof(I)) * (size_t)GROUPS * TABLE;
   auto kern = num_hash_kernel<V, I, TABLE, THREADS, WARP>;
@@ -573,7 +652,7 @@ static int launch_num_hash(int64_t n, const int32_t* list, const int64_t* a_ptr,
     attr = true;
   }
   kern<<<(unsigned)ceil_div(n, GROUPS), THREADS, smem, st>>>(n, list, a_ptr, a_col, a_val, b_ptr, b_col,
-                                                            b_val, c_ptr, c_col, c_val);
+                                                            b_val, c_ptr, c_col, c_val, gs);
   B2S_CHECK_LAUNCH();
   return B2S_OK;
 }
@@ -581,7 +660,8 @@ static int launch_num_hash(int64_t n, const int32_t* list, const int64_t* a_ptr,
 template <typename V, typename I>
 static int numeric_typed(int64_t nrowsA, int64_t ncolsB, const int64_t* a_ptr, const I* a_col,
                          const V* a_val, const int64_t* b_ptr, const I* b_col, const V* b_val,
-                         const int64_t* c_ptr, I* c_col, V* c_val, void* workspace, cudaStream_t st) {
+                         const int64_t* c_ptr, I* c_col, V* c_val, void* workspace, int gs,
+                         cudaStream_t st) {
   if (nrowsA == 0) return B2S_OK;
   SpgemmWs W = carve_ws(workspace, nrowsA);
   B2S_CUDA_TRY(cudaMemsetAsync(W.counters, 0, 16 * 8, st));
@@ -592,17 +672,17 @@ static int numeric_typed(int64_t nrowsA, int64_t ncolsB, const int64_t* a_ptr, c
   if (rc) return rc;
   if (cc.n[1] > 0) {
     rc = launch_num_hash<V, I, kT1, 256, true>(cc.n[1], W.list[1], a_ptr, a_col, a_val, b_ptr, b_col, b_val,
-                                               c_ptr, c_col, c_val, st);
+                                               c_ptr, c_col, c_val, gs, st);
     if (rc) return rc;
   }
   if (cc.n[2] > 0) {
     rc = launch_num_hash<V, I, kT2, 128, false>(cc.n[2], W.list[2], a_ptr, a_col, a_val, b_ptr, b_col, b_val,
-                                                c_ptr, c_col, c_val, st);
+                                                c_ptr, c_col, c_val, gs, st);
     if (rc) return rc;
   }
   if (cc.n[3] > 0) {
     rc = launch_num_hash<V, I, kT3, 512, false>(cc.n[3], W.list[3], a_ptr, a_col, a_val, b_ptr, b_col, b_val,
-                                                c_ptr, c_col, c_val, st);
+                                                c_ptr, c_col, c_val, gs, st);
     if (rc) return rc;
   }
   if (cc.n[4] > 0) {
@@ -645,7 +725,7 @@ extern "C" int b2s_spgemm_symbolic(b2s_itype it, int64_t nrowsA, int64_t ncolsA,
   cudaStream_t st = (cudaStream_t)stream;
   B2S_DISPATCH_IT(it, I,
     return symbolic_typed<I>(nrowsA, ncolsB, a_indptr, (const I*)a_indices, b_indptr, (const I*)b_indices,
-                             c_indptr, workspace, out_nnzC, out_products, st));
+                             c_indptr, workspace, out_nnzC, out_products, lane_group_size(nnzB, ncolsA), st));
   return B2S_ERR_ARG;
 }
 
@@ -666,6 +746,6 @@ extern "C" int b2s_spgemm_numeric(b2s_dtype vt, b2s_itype it, int64_t nrowsA, in
   B2S_DISPATCH_VT(vt, V, B2S_DISPATCH_IT(it, I,
     return numeric_typed<V, I>(nrowsA, ncolsB, a_indptr, (const I*)a_indices, (const V*)a_data, b_indptr,
                                (const I*)b_indices, (const V*)b_data, c_indptr, (I*)c_indices,
-                               (V*)c_data, workspace, st)));
+                               (V*)c_data, workspace, lane_group_size(nnzB, ncolsA), st)));
   return B2S_ERR_ARG;
 }

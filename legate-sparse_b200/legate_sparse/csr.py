@@ -792,6 +792,20 @@ def spgemm_csr_csr_csr(A: csr_array, B: csr_array) -> csr_array:
     itype = N.B2S_I32 if a_idx.dtype == torch.int32 else N.B2S_I64
     nA, kA, nB = blk.nrows, A.shape[1], B.shape[1]
     nnzB = int(b_dat.numel())
+    import os as _os
+    import time as _time
+
+    _timing = _os.environ.get("B2S_SPGEMM_TIMING") is not None   # phase timings (adds syncs)
+
+    def _tick(label, t_prev):
+        if not _timing:
+            return t_prev
+        torch.cuda.synchronize()
+        now = _time.perf_counter()
+        print(f"[spgemm] {label}: {(now - t_prev) * 1e3:.3f} ms")
+        return now
+
+    _t = _tick("start", _time.perf_counter())
     ws_bytes = int(lib.b2s_spgemm_workspace_bytes(nA, blk.nnz, nB))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     c_ptr = torch.empty(nA + 1, dtype=torch.int64, device=dev)
@@ -801,14 +815,17 @@ def spgemm_csr_csr_csr(A: csr_array, B: csr_array) -> csr_array:
                                 nnzB, ptr(c_ptr), ptr(ws), ws_bytes, byref(nnzC), byref(products), stream_ptr()),
         "spgemm_symbolic",
     )
+    _t = _tick("alloc ws + symbolic", _t)
     c_idx = torch.empty(nnzC.value, dtype=a_idx.dtype, device=dev)
     c_dat = torch.empty(nnzC.value, dtype=blk.data.dtype, device=dev)
+    _t = _tick("alloc C", _t)
     N.check(
         lib.b2s_spgemm_numeric(vt_enum(A.dtype), itype, nA, kA, nB, ptr(blk.indptr), ptr(a_idx), ptr(blk.data),
                                blk.nnz, ptr(b_ptr), ptr(b_idx), ptr(b_dat), nnzB, ptr(c_ptr), ptr(c_idx),
                                ptr(c_dat), ptr(ws), ws_bytes, stream_ptr()),
         "spgemm_numeric",
     )
+    _t = _tick("numeric", _t)
     shape = (A.shape[0], B.shape[1])
     G = dist.world_size()
     if G == 1:
