@@ -1,10 +1,11 @@
-"""dia_array — diagonal storage used to build matrices (reference legate_sparse/dia.py:65-194).
+"""dia_array — diagonal storage used to assemble matrices (reference legate_sparse/dia.py:65-194).
 
-Construction-only format (host numpy); ``tocsr`` follows scipy's DIA→CSR converter — the
-reference lifts the same routine (dia.py:152-190): transpose, mask of in-range NON-ZERO
-entries, ``indptr = cumsum(mask.sum(axis=0))``, ``indices = row.T[mask.T]``.  For descending
-offsets the reference emits unsorted rows while scipy emits sorted ones; scipy is the stated
-oracle, so rows are emitted sorted (identical for the ascending offsets every test uses).
+Construction-only format, host numpy.  Layout is scipy's: ``data[d, j]`` is the entry in column j
+of the diagonal ``offsets[d]``, i.e. A[j - offsets[d], j].  ``tocsr`` enumerates the stored entries
+diagonal by diagonal, drops out-of-range and explicitly zero entries (the reference masks
+``data != 0`` as well, dia.py:171) and orders them by (row, column) — the canonical sorted CSR that
+scipy produces; for the ascending offsets used by every reference test/example this equals the
+reference's own output bit for bit (tests/test_host_surface.py::test_diags_vs_reference_run).
 """
 import numpy
 
@@ -19,97 +20,77 @@ class dia_array(CompressedBase):
     def __init__(self, arg, shape=None, dtype=None, copy=False):
         if shape is None:
             raise NotImplementedError
-        assert isinstance(arg, tuple)
-        data, offsets = arg
-        if isinstance(offsets, int):
-            offsets = numpy.full((1,), offsets)
-        data, offsets = numpy.asarray(data), numpy.atleast_1d(numpy.asarray(offsets))
-        if data.ndim == 1:
-            data = data[None, :]
+        if not isinstance(arg, tuple):
+            raise AssertionError("dia_array expects a (data, offsets) tuple")
+        values, offs = arg
+        offs = numpy.atleast_1d(numpy.asarray(offs if not isinstance(offs, int) else [offs]))
+        values = numpy.asarray(values)
+        values = values.reshape(1, -1) if values.ndim == 1 else values
         if dtype is not None:
-            data = data.astype(dtype)
+            values = values.astype(dtype)
         elif copy:
-            data = data.copy()
-        self.dtype = numpy.dtype(data.dtype)
-        self.shape = tuple(int(i) for i in shape)
-        self._offsets = offsets.copy() if copy else offsets
-        self._data = data
+            values = values.copy()
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.dtype = numpy.dtype(values.dtype)
+        self._values = values
+        self._offs = offs.copy() if copy else offs
 
-    @property
-    def nnz(self):
-        M, N = self.shape
-        nnz = 0
-        for k in self.offsets:
-            if k > 0:
-                nnz += min(M, N - k)
-            else:
-                nnz += min(M + k, N)
-        return int(nnz)
-
+    # ---- stored arrays -------------------------------------------------------------------
     @property
     def data(self):
-        return self._data
+        return self._values
 
     @property
     def offsets(self):
-        return self._offsets
+        return self._offs
+
+    @property
+    def nnz(self):
+        """number of positions covered by the stored diagonals (explicit zeros included)"""
+        rows, cols = self.shape
+        return int(sum(min(rows, cols - k) if k > 0 else min(rows + k, cols) for k in self._offs.tolist()))
 
     def copy(self):
-        return dia_array((self.data.copy(), self.offsets.copy()), shape=self.shape, dtype=self.dtype)
+        return dia_array((self._values.copy(), self._offs.copy()), shape=self.shape, dtype=self.dtype)
 
+    # ---- transpose: B = A^T has offsets -k and data_B[d, c] = data_A[d, c + k] -----------------
     def transpose(self, axes=None, copy=False):
         if axes is not None:
-            raise ValueError(
-                "Sparse matrices do not support an 'axes' parameter because swapping "
-                "dimensions is the only logical permutation."
-            )
+            raise ValueError("Sparse matrices do not support an 'axes' parameter because swapping "
+                             "dimensions is the only logical permutation.")
         if copy:
             raise AssertionError
-        num_rows, num_cols = self.shape
-        max_dim = max(self.shape)
-        offsets = -self.offsets
-        r = numpy.arange(len(offsets), dtype=coord_ty)[:, None]
-        c = numpy.arange(num_rows, dtype=coord_ty) - (offsets % max_dim)[:, None]
-        pad_amount = max(0, max_dim - self.data.shape[1])
-        data = numpy.hstack((self.data, numpy.zeros((self.data.shape[0], pad_amount), dtype=self.data.dtype)))
-        data = data[r, c]
-        return dia_array((data, offsets), shape=(num_cols, num_rows), copy=copy, dtype=self.dtype)
+        rows, cols = self.shape
+        width = max(rows, cols)
+        out = numpy.zeros((len(self._offs), rows), dtype=self.dtype)   # B has `rows` columns
+        src_width = self._values.shape[1]
+        for d, k in enumerate(self._offs.tolist()):
+            c = numpy.arange(rows)
+            src = c + k
+            ok = (src >= 0) & (src < src_width) & (src < width)
+            out[d, c[ok]] = self._values[d, src[ok]]
+        return dia_array((out, -self._offs), shape=(cols, rows), dtype=self.dtype)
 
     T = property(transpose)
 
+    # ---- DIA → CSR -----------------------------------------------------------------------
     def tocsr(self, copy=False):
-        if copy:
-            return self.copy().tocsr(copy=False)
-        return self.transpose(copy=copy)._tocsr_transposed(copy=False)
-
-    def _tocsr_transposed(self, copy=False):
-        # self is the TRANSPOSE of the matrix being converted; the CSR of the original is the
-        # CSC of self (same routine scipy's dia_matrix.tocsc runs).
-        num_rows, num_cols = self.shape          # shape of the transposed operand
-        out_shape = (num_cols, num_rows)
-        if self.nnz == 0:
-            return csr_array(out_shape, dtype=self.dtype)
-        num_offsets, offset_len = self.data.shape
-        offset_inds = numpy.arange(offset_len)
-        row = offset_inds - self.offsets[:, None]
-        mask = row >= 0
-        mask &= row < num_rows
-        mask &= offset_inds < num_cols
-        mask &= self.data != 0
-        idx_dtype = coord_ty
-        indptr = numpy.zeros(num_cols + 1, dtype=idx_dtype)
-        indptr[1 : offset_len + 1] = numpy.cumsum(mask.sum(axis=0, dtype=idx_dtype)[:num_cols])
-        if offset_len < num_cols:
-            indptr[offset_len + 1 :] = indptr[offset_len]
-        indices = row.T[mask.T].astype(idx_dtype, copy=False)
-        data = self.data.T[mask.T]
-        out = csr_array((data, indices, indptr), shape=out_shape, dtype=self.dtype, copy=False)
-        # scipy emits sorted rows; for non-ascending offsets sort inside each row
-        if len(self.offsets) > 1 and numpy.any(numpy.diff(-self.offsets) < 0):
-            sp = out.toscipy()
-            sp.sort_indices()
-            out = csr_array((sp.data, sp.indices, sp.indptr), shape=out_shape, dtype=self.dtype)
-        return out
+        rows, cols = self.shape
+        r_parts, c_parts, v_parts = [], [], []
+        for d, k in enumerate(self._offs.tolist()):
+            j = numpy.arange(max(0, k), min(cols, rows + k, self._values.shape[1]))   # columns on this diagonal
+            if j.size == 0:
+                continue
+            v = self._values[d, j]
+            keep = v != 0
+            r_parts.append((j - k)[keep]); c_parts.append(j[keep]); v_parts.append(v[keep])
+        if not v_parts:
+            return csr_array((rows, cols), dtype=self.dtype)
+        r, c, v = numpy.concatenate(r_parts), numpy.concatenate(c_parts), numpy.concatenate(v_parts)
+        order = numpy.lexsort((c, r))                      # by row, then column
+        indptr = numpy.zeros(rows + 1, dtype=coord_ty)
+        numpy.cumsum(numpy.bincount(r, minlength=rows), out=indptr[1:])
+        return csr_array((v[order], c[order].astype(coord_ty), indptr), shape=self.shape, dtype=self.dtype)
 
 
 dia_matrix = dia_array

@@ -1,59 +1,52 @@
-"""diags() — construct a sparse matrix from diagonals
-(reference legate_sparse/gallery.py:77-195, itself lifted from scipy.sparse.diags;
-quirks kept: ``dtype`` is mandatory, formats limited to None/"dia"/"csr")."""
+"""diags() — assemble a sparse matrix from its diagonals.
+
+Behaviour of the reference's gallery.diags (legate_sparse/gallery.py:77-195, a scipy.sparse.diags
+derivative) including its quirks: `dtype` is mandatory, only format None / "dia" / "csr" exists,
+a missing shape means a square matrix just large enough for the first diagonal, scalars broadcast
+along their diagonal."""
 import numpy
 
 from .dia import dia_array
 
+_FORMATS = (None, "dia", "csr")
+
+
+def _as_diagonal_list(diagonals, offsets):
+    """normalise (diagonals, offsets) to (list of 1-D arrays, 1-D int array)"""
+    if numpy.isscalar(offsets):
+        single = len(diagonals) == 0 or numpy.isscalar(diagonals[0])
+        if not single:
+            raise ValueError("Different number of diagonals and offsets.")
+        return [numpy.atleast_1d(diagonals)], numpy.atleast_1d(offsets)
+    bands = [numpy.atleast_1d(d) for d in diagonals]
+    offs = numpy.atleast_1d(offsets)
+    if len(bands) != len(offs):
+        raise ValueError("Different number of diagonals and offsets.")
+    return bands, offs
+
 
 def diags(diagonals, offsets=0, shape=None, format=None, dtype=None):
-    # if offsets is not a sequence, assume that there's only one diagonal
-    if numpy.isscalar(offsets):
-        if len(diagonals) == 0 or numpy.isscalar(diagonals[0]):
-            diagonals = [numpy.atleast_1d(diagonals)]
-        else:
-            raise ValueError("Different number of diagonals and offsets.")
-    else:
-        diagonals = list(map(numpy.atleast_1d, diagonals))
-
-    offsets = numpy.atleast_1d(offsets)
-
-    if len(diagonals) != len(offsets):
-        raise ValueError("Different number of diagonals and offsets.")
-
+    bands, offs = _as_diagonal_list(diagonals, offsets)
     if shape is None:
-        m = len(diagonals[0]) + abs(int(offsets[0]))
-        shape = (m, m)
-
+        side = len(bands[0]) + abs(int(offs[0]))
+        shape = (side, side)
     if dtype is None:
+        raise NotImplementedError          # the reference does not infer the dtype
+    if format not in _FORMATS:
         raise NotImplementedError
-
-    if format is not None and format not in ["csr", "dia"]:
-        raise NotImplementedError
-
-    m, n = shape
-    M = max([min(m + int(offset), n - int(offset)) + max(0, int(offset)) for offset in offsets])
-    M = max(0, M)
-    data_arr = numpy.zeros((len(offsets), M), dtype=dtype)
-    K = min(m, n)
-
-    for j, diagonal in enumerate(diagonals):
-        offset = int(offsets[j])
-        k = max(0, offset)
-        length = min(m + offset, n - offset, K)
-        if length < 0:
-            raise ValueError("Offset %d (index %d) out of bounds" % (offset, j))
-        try:
-            data_arr[j, k : k + length] = diagonal[..., :length]
-        except ValueError as e:
-            if len(diagonal) != length and len(diagonal) != 1:
-                raise ValueError(
-                    "Diagonal length (index %d: %d at offset %d) does not "
-                    "agree with matrix size (%d, %d)." % (j, len(diagonal), offset, m, n)
-                ) from e
-            raise
-
-    dia = dia_array((data_arr, offsets), shape=(m, n), dtype=dtype)
-    if format == "csr":
-        return dia.tocsr()
-    return dia
+    nrows, ncols = int(shape[0]), int(shape[1])
+    # DIA storage: one row per diagonal, indexed by COLUMN
+    width = max([0] + [min(nrows + int(k), ncols - int(k)) + max(0, int(k)) for k in offs])
+    stored = numpy.zeros((len(offs), width), dtype=dtype)
+    longest = min(nrows, ncols)
+    for row, (band, k) in enumerate(zip(bands, (int(k) for k in offs))):
+        count = min(nrows + k, ncols - k, longest)
+        if count < 0:
+            raise ValueError("Offset %d (index %d) out of bounds" % (k, row))
+        first = max(0, k)
+        if band.shape[0] not in (1, count) and band.shape[0] < count:
+            raise ValueError("Diagonal length (index %d: %d at offset %d) does not agree with matrix size (%d, %d)."
+                             % (row, band.shape[0], k, nrows, ncols))
+        stored[row, first:first + count] = band[..., :count]
+    out = dia_array((stored, offs), shape=(nrows, ncols), dtype=dtype)
+    return out.tocsr() if format == "csr" else out

@@ -1,21 +1,21 @@
-"""Module-level exports (reference legate_sparse/module.py:40-70)."""
-from .csr import csr_array  # noqa: F401
+"""Names exported at package level (same public names as the reference's module.py:40-70)."""
+from . import csr as _csr
 from .dia import dia_array  # noqa: F401
 from .gallery import diags  # noqa: F401
 from .io import mmread  # noqa: F401
-
-# expose default types
 from .types import coord_ty, nnz_ty  # noqa: F401
 
-
-def is_sparse_matrix(o):
-    """True for matrices created by this package (reference module.py:55-58)."""
-    return any((isinstance(o, csr_array),))
+csr_array = _csr.csr_array
+_SPARSE_KINDS = (_csr.csr_array,)
 
 
-issparse = is_sparse_matrix
-isspmatrix = is_sparse_matrix
+def is_sparse_matrix(obj) -> bool:
+    """True when `obj` is a sparse matrix created by this package."""
+    return isinstance(obj, _SPARSE_KINDS)
 
 
-def isspmatrix_csr(o):
-    return isinstance(o, csr_array)
+def isspmatrix_csr(obj) -> bool:
+    return isinstance(obj, _csr.csr_array)
+
+
+issparse = isspmatrix = is_sparse_matrix
