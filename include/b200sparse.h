@@ -121,6 +121,39 @@ int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, i
                      void* dot_out, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Column-blocked operand for SpMV when x does not stay L2-resident (ncols * sizeof(value) well
+ * above ~40 MB and rows that reach across all of x — the random C2 matrix of BASELINE.json).
+ * Same role as the cuSPARSE preprocess/buffer step of the reference's SpMV task
+ * (src/legate_sparse/array/csr/spmv.cu:27-75): a one-time layout, cached next to the plan.
+ * A = [A_0 | A_1 | ...] by column ranges of `block_cols`; y = A_0 x; y += A_1 x; ... — one pipe
+ * kernel launch per block, each gathering from one slice of x.  The object keeps device
+ * pointers into `workspace` (caller-owned, must outlive it) and a COPY of the values: rebuild it
+ * when the matrix values change.
+ * ------------------------------------------------------------------------ */
+typedef struct b2s_colblock b2s_colblock; /* opaque, host object */
+
+/* Heuristic: *out_nblocks = 1 → not worthwhile; otherwise the number of blocks to build.
+ * Samples row spans on the device (synchronises the stream).  B2S_SPMV_COLBLOCK=0 disables,
+ * =N forces N blocks; B2S_COLBLOCK_MB sets the x-slice size (default 40). */
+int b2s_csr_colblock_suggest(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                             const int64_t* indptr, const void* indices, b2s_stream_t stream,
+                             int* out_nblocks);
+int64_t b2s_csr_colblock_workspace_bytes(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t nnz,
+                                         int nblocks);
+/* nblocks in [2,32].  Entries keep their order within a row (stable split). */
+int b2s_csr_colblock_create(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                            const int64_t* indptr, const void* indices, const void* data,
+                            int nblocks, void* workspace, int64_t workspace_bytes,
+                            b2s_stream_t stream, b2s_colblock** out);
+void b2s_csr_colblock_destroy(b2s_colblock* cb);
+int b2s_csr_colblock_info(const b2s_colblock* cb, int* nblocks, int64_t* block_cols,
+                          int64_t* blk_nnz /* [nblocks] or NULL */);
+/* y = A x over the blocks.  Optional fused dot (w, dot_out as in b2s_spmv_csr_dot) and peer
+ * broadcast (y_peers, npeers as in b2s_spmv_csr_bcast) are applied by the last block's launch. */
+int b2s_spmv_colblock(const b2s_colblock* cb, const void* x, void* y, const void* w, void* dot_out,
+                      void* const* y_peers, int npeers, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Dense vector kernels of the CG/GMRES loop.
  * ---------------------------------------------------------------------- */
 /* AXPBY task: src/sparse/linalg/axpby.cu:25-66, axpby_template.inl:30-71.

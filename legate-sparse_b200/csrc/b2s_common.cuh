@@ -342,6 +342,19 @@ __device__ __forceinline__ void store_bcast(V* __restrict__ y, const PeerOut<V>&
 // ---------------------------------------------------------------- misc
 __host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---------------------------------------------------------------- cross-TU internals (not in the C ABI)
+// b2s_spgemm.cu: in-place inclusive scan of v[0..n), first[0] = 0; blocksum = ceil(n/1024)+1 int64 scratch
+int scan_inclusive_i64(int64_t n, int64_t* v, int64_t* first, int64_t* blocksum, cudaStream_t st);
+// b2s_spmv.cu: the one SpMV entry (accumulate != 0: y += A x, pipe kernel only)
+int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+               const int64_t* indptr, const void* indices, const void* data, const void* x, void* y,
+               const b2s_spmv_plan* plan, int variant, void* dot_out, void* partials, const void* w,
+               void* const* y_peers, int npeers, int accumulate, b2s_stream_t stream);
+int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* indptr,
+                     const void* indices, void* workspace, int64_t workspace_bytes, b2s_stream_t stream,
+                     int64_t force_tile, b2s_spmv_plan** out_plan);
+void* plan_dot_partials(const b2s_spmv_plan* plan);
+
 template <typename I> struct it_code;
 template <> struct it_code<int32_t> { static constexpr b2s_itype value = B2S_I32; };
 template <> struct it_code<int64_t> { static constexpr b2s_itype value = B2S_I64; };

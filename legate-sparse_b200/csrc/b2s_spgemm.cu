@@ -216,6 +216,21 @@ __global__ void scan_add_kernel(int64_t n, int64_t* __restrict__ out_incl, const
   if (i < n && blockIdx.x > 0) out_incl[i] += blocksum[blockIdx.x - 1];
 }
 
+// v[0..n) → inclusive prefix sums in place, first[0] = 0 (first is normally v-1: an indptr).
+// blocksum: scratch of ceil(n/1024)+1 int64.  Shared with the column-block splitter.
+int scan_inclusive_i64(int64_t n, int64_t* v, int64_t* first, int64_t* blocksum, cudaStream_t st) {
+  int64_t nb = ceil_div(n > 0 ? n : 1, kScanBlock);
+  scan_block_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(n, v, v, blocksum);
+  B2S_CHECK_LAUNCH();
+  if (nb > 1) {
+    scan_sums_kernel<<<1, kScanBlock, 0, st>>>(nb, blocksum);
+    B2S_CHECK_LAUNCH();
+  }
+  scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(n, v, blocksum, first);
+  B2S_CHECK_LAUNCH();
+  return B2S_OK;
+}
+
 // ------------------------------------------------------------------ hash kernels (symbolic)
 // One group (warp when WARP_ROWS>1, else the CTA) per row.
 template <typename I, int TABLE, int THREADS, bool WARP_PER_ROW>
@@ -621,15 +636,7 @@ static int symbolic_typed(int64_t nrowsA, int64_t ncolsB, const int64_t* a_ptr, 
     B2S_CHECK_LAUNCH();
   }
   // inclusive scan of row_nnz in place → c_ptr[1..nrows]; c_ptr[0] = 0
-  int64_t nb = ceil_div(nrowsA, kScanBlock);
-  scan_block_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(nrowsA, row_nnz, row_nnz, W.blocksum);
-  B2S_CHECK_LAUNCH();
-  if (nb > 1) {
-    scan_sums_kernel<<<1, kScanBlock, 0, st>>>(nb, W.blocksum);
-    B2S_CHECK_LAUNCH();
-  }
-  scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(nrowsA, row_nnz, W.blocksum, c_ptr);
-  B2S_CHECK_LAUNCH();
+  { int rc2 = scan_inclusive_i64(nrowsA, row_nnz, c_ptr, W.blocksum, st); if (rc2) return rc2; }
   int64_t nnzC = 0;
   B2S_CUDA_TRY(cudaMemcpyAsync(&nnzC, c_ptr + nrowsA, 8, cudaMemcpyDeviceToHost, st));
   free_dense(&D, st);

@@ -344,13 +344,13 @@ static int num_sms() {
   return n;
 }
 
-template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool ROWWALK>
+template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool BCAST>
 static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                            const PeerOut<V>& peers, cudaStream_t st) {
+                            const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
   using L = PipeLayout<V, I, IPT>;
   const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
-  auto kern = spmv_pipe_kernel<V, I, IPT, STAGES, WINDOW, DOT, ROWWALK>;
+  auto kern = spmv_pipe_kernel<V, I, IPT, STAGES, WINDOW, DOT, BCAST>;
   static int blocks_per_sm = -1;  // per instantiation
   if (blocks_per_sm < 0) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -364,7 +364,8 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   *npartials = grid;
   kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals,
                                                    x, y, P->tile_row, P->tile_win,
-                                                   reinterpret_cast<V*>(P->head), dot_partials, w, peers);
+                                                   reinterpret_cast<V*>(P->head), dot_partials, w, peers,
+                                                   accumulate);
   B2S_CHECK_LAUNCH();
   return B2S_OK;
 }
@@ -439,15 +440,16 @@ static int pipe_stages_default(int ipt) {
 template <typename V, typename I, int IPT, bool DOT>
 static int launch_pipe_ipt(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                            const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                           const PeerOut<V>& peers, cudaStream_t st) {
+                           const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
   bool window = (P->window_tiles * 2 >= P->ntiles) && ((uintptr_t)x % 16 == 0) &&
                 getenv("B2S_SPMV_NO_WINDOW") == nullptr;
-  // window matrices (banded / stencil): row-walk consumer; others: products consumer.
-  // Only STAGES = 2 is instantiated (deeper rings cost CTAs/SM and measured slower).
-  const bool rowwalk = window ? (getenv("B2S_SPMV_PRODUCTS") == nullptr) : (getenv("B2S_SPMV_ROWWALK") != nullptr);
-#define B2S_PIPE(W, R) launch_pipe_inst<V, I, IPT, 2, W, DOT, R>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, st)
-  if (window) return rowwalk ? B2S_PIPE(true, true) : B2S_PIPE(true, false);
-  return rowwalk ? B2S_PIPE(false, true) : B2S_PIPE(false, false);
+  // window matrices (banded / stencil): row-walk consumer; others: products consumer (chosen by
+  // WINDOW inside the kernel).  Only STAGES = 2 is instantiated (deeper rings cost CTAs/SM and
+  // measured slower).  Peer stores are compiled in only for the broadcast launches.
+  const bool bcast = peers.n != 0;
+#define B2S_PIPE(W, B) launch_pipe_inst<V, I, IPT, 2, W, DOT, B>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, accumulate, st)
+  if (window) return bcast ? B2S_PIPE(true, true) : B2S_PIPE(true, false);
+  return bcast ? B2S_PIPE(false, true) : B2S_PIPE(false, false);
 #undef B2S_PIPE
 }
 
@@ -504,7 +506,7 @@ static int launch_tile_ipt(const PlanHeader* P, const int64_t* indptr, const I* 
 template <typename V, typename I, bool DOT>
 static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                     const V* x, V* y, V* dot_out, V* dot_partials, const V* w, int mode,
-                    const PeerOut<V>& peers, cudaStream_t st) {
+                    const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
   int rc;
   int64_t npartials = P->ntiles;
   if (mode == 3) {
@@ -528,8 +530,8 @@ static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, c
     }
     return B2S_OK;   // the merge path has its own fix-up (sub-tile granularity)
   } else if (mode == 1) {
-    if (P->tile_nnz == 1024) rc = launch_pipe_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, st);
-    else                     rc = launch_pipe_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, st);
+    if (P->tile_nnz == 1024) rc = launch_pipe_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, accumulate, st);
+    else                     rc = launch_pipe_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, accumulate, st);
   } else
   switch (P->tile_nnz) {
     case 1024: rc = launch_tile_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, st); break;
@@ -586,15 +588,18 @@ __global__ void fill_zero_kernel(int64_t n, V* y) {
 template <typename V, typename I>
 static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* indptr, const I* cols,
                       const V* vals, const V* x, V* y, const PlanHeader* P, int variant, V* dot_out,
-                      V* dot_partials, const V* w, const PeerOut<V>& peers, cudaStream_t st) {
+                      V* dot_partials, const V* w, const PeerOut<V>& peers, int accumulate,
+                      cudaStream_t st) {
   const bool want_dot = dot_out != nullptr;
   if (nrows == 0) {
     if (want_dot) { fill_zero_kernel<V><<<1, 32, 0, st>>>(1, dot_out); B2S_CHECK_LAUNCH(); }
     return B2S_OK;
   }
   if (nnz == 0) {
-    fill_zero_kernel<V><<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(nrows, y);
-    B2S_CHECK_LAUNCH();
+    if (!accumulate) {
+      fill_zero_kernel<V><<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(nrows, y);
+      B2S_CHECK_LAUNCH();
+    }
     if (want_dot) { fill_zero_kernel<V><<<1, 32, 0, st>>>(1, dot_out); B2S_CHECK_LAUNCH(); }
     return B2S_OK;
   }
@@ -630,11 +635,15 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
       set_error("peer broadcast needs the pipe kernel (16-byte aligned arrays, 1024/2048-nnz plan)");
       return B2S_ERR_UNSUPPORTED;
     }
-    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, peers, st);
-    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, peers, st);
+    if (accumulate && mode != 1) {
+      set_error("y += A x needs the pipe kernel (16-byte aligned arrays, 1024/2048-nnz plan)");
+      return B2S_ERR_UNSUPPORTED;
+    }
+    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, peers, accumulate, st);
+    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, peers, accumulate, st);
   }
-  if (peers.n != 0) {
-    set_error("peer broadcast needs a plan");
+  if (peers.n != 0 || accumulate) {
+    set_error("peer broadcast / accumulate need a plan");
     return B2S_ERR_UNSUPPORTED;
   }
   return run_rowvec<V, I>(nrows, nnz, indptr, cols, vals, x, y, st);
@@ -653,10 +662,12 @@ extern "C" int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz) {
   return (ntiles + 1) * 8 + ntiles * 16 + ntiles * 16 + ntiles * 16 + ntiles * 8 * 24 + (ntiles * 8 + 4) * 8 + 64 + 1024;
 }
 
-extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
-                                    const int64_t* indptr, const void* indices, void* workspace,
-                                    int64_t workspace_bytes, b2s_stream_t stream,
-                                    b2s_spmv_plan** out_plan) {
+namespace b2s {
+// force_tile: 0 = automatic (env B2S_SPMV_TILE_NNZ, else 2048 with a 1024 re-plan when not window-friendly)
+int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                     const int64_t* indptr, const void* indices, void* workspace,
+                     int64_t workspace_bytes, b2s_stream_t stream, int64_t force_tile,
+                     b2s_spmv_plan** out_plan) {
   B2S_REQUIRE(out_plan != nullptr, "out_plan is null");
   *out_plan = nullptr;
   B2S_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative size");
@@ -674,8 +685,8 @@ extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, 
   // Tile size: an explicit B2S_SPMV_TILE_NNZ wins; otherwise plan with 2048-nnz tiles first and,
   // when the matrix is not window-friendly (x gathers must go to L2), re-plan with 1024-nnz tiles
   // (the configuration each consumer flavour measured fastest with on B200).
-  const bool forced = getenv("B2S_SPMV_TILE_NNZ") != nullptr;
-  int64_t candidates[2] = {forced ? default_tile_nnz() : 2048, 1024};
+  const bool forced = getenv("B2S_SPMV_TILE_NNZ") != nullptr || force_tile > 0;
+  int64_t candidates[2] = {getenv("B2S_SPMV_TILE_NNZ") ? default_tile_nnz() : (force_tile > 0 ? force_tile : 2048), 1024};
   for (int attempt = 0; attempt < 2; ++attempt) {
     P->tile_nnz = candidates[attempt];
     P->ntiles = ceil_div(nnz, P->tile_nnz);
@@ -733,6 +744,15 @@ extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, 
   *out_plan = P;
   return B2S_OK;
 }
+}  // namespace b2s
+
+extern "C" int b2s_spmv_plan_create(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                                    const int64_t* indptr, const void* indices, void* workspace,
+                                    int64_t workspace_bytes, b2s_stream_t stream,
+                                    b2s_spmv_plan** out_plan) {
+  return plan_create_impl(it, nrows, ncols, nnz, indptr, indices, workspace, workspace_bytes, stream, 0,
+                          out_plan);
+}
 
 extern "C" void b2s_spmv_plan_destroy(b2s_spmv_plan* plan) { delete plan; }
 
@@ -745,10 +765,11 @@ extern "C" int b2s_spmv_plan_info(const b2s_spmv_plan* plan, int64_t* ntiles, in
   return B2S_OK;
 }
 
-static int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
-                      const int64_t* indptr, const void* indices, const void* data, const void* x,
-                      void* y, const b2s_spmv_plan* plan, int variant, void* dot_out, void* partials,
-                      const void* w, void* const* y_peers, int npeers, b2s_stream_t stream) {
+namespace b2s {
+int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+               const int64_t* indptr, const void* indices, const void* data, const void* x,
+               void* y, const b2s_spmv_plan* plan, int variant, void* dot_out, void* partials,
+               const void* w, void* const* y_peers, int npeers, int accumulate, b2s_stream_t stream) {
   B2S_REQUIRE(npeers >= -1 && npeers <= kMaxPeers, "npeers must be in [-1,7]");
   B2S_REQUIRE(npeers == 0 || y_peers != nullptr, "y_peers is null");
   B2S_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative size");
@@ -764,17 +785,19 @@ static int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, 
     B2S_DISPATCH_IT(it, I,
       return spmv_typed<V, I>(nrows, ncols, nnz, indptr, (const I*)indices, (const V*)data,
                               (const V*)x, (V*)y, plan, variant, (V*)dot_out, (V*)partials, (const V*)w,
-                              peers, st));
+                              peers, accumulate, st));
   });
   return B2S_ERR_ARG;
 }
+void* plan_dot_partials(const b2s_spmv_plan* plan) { return plan->dotp; }
+}  // namespace b2s
 
 extern "C" int b2s_spmv_csr(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
                             const int64_t* indptr, const void* indices, const void* data,
                             const void* x, void* y, const b2s_spmv_plan* plan, int variant,
                             b2s_stream_t stream) {
   return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, variant, nullptr,
-                    nullptr, nullptr, nullptr, 0, stream);
+                    nullptr, nullptr, nullptr, 0, 0, stream);
 }
 
 extern "C" int b2s_spmv_csr_bcast(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
@@ -783,7 +806,7 @@ extern "C" int b2s_spmv_csr_bcast(b2s_dtype vt, b2s_itype it, int64_t nrows, int
                                   const b2s_spmv_plan* plan, b2s_stream_t stream) {
   B2S_REQUIRE(plan != nullptr, "broadcast SpMV needs a plan");
   return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO, nullptr,
-                    nullptr, nullptr, y_peers, npeers, stream);
+                    nullptr, nullptr, y_peers, npeers, 0, stream);
 }
 
 extern "C" int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
@@ -794,5 +817,5 @@ extern "C" int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64
   B2S_REQUIRE(nrows == 0 || w != nullptr, "w null");
   B2S_REQUIRE(plan != nullptr, "fused dot needs a plan");
   return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO,
-                    dot_out, plan->dotp, w, nullptr, 0, stream);
+                    dot_out, plan->dotp, w, nullptr, 0, 0, stream);
 }

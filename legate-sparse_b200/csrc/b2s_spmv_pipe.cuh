@@ -55,16 +55,21 @@ __device__ __forceinline__ void consumer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumers) : "memory");
 }
 
-template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool ROWWALK>
+// WINDOW also selects the consumer: window matrices (banded / stencil) use the row-walk consumer,
+// all others the products consumer (each measured fastest there; the cross combinations were never
+// faster and are not instantiated).  BCAST compiles the peer stores in; the plain instances carry
+// no trace of them (the peer ranges cost the banded kernel 13% when they were a runtime branch).
+template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool BCAST>
 __global__ void __launch_bounds__(kPipeThreads)
 spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const int64_t* __restrict__ indptr, const I* __restrict__ cols,
                  const V* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
                  const int64_t* __restrict__ tile_row, const int64_t* __restrict__ tile_win,
                  V* __restrict__ head, V* __restrict__ dot_partials, const V* __restrict__ w,
-                 const PeerOut<V> peers) {
+                 const PeerOut<V> peers, const int accumulate) {
   using L = PipeLayout<V, I, IPT>;
   constexpr int T = L::T;
+  constexpr bool ROWWALK = WINDOW;
   constexpr size_t STAGE = L::stage_bytes(WINDOW);
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + STAGE * STAGES);
@@ -210,7 +215,11 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         if (valid && gl == 0) {
           bool wrote = false;
           if (lo_g < S) { head[t] = sum; wrote = true; }
-          else if (r < r_last || lo_g < E) { store_bcast(y, peers, r, sum); wrote = true; }
+          else if (r < r_last || lo_g < E) {
+            if (accumulate) sum = vadd(sum, y[r]);   // y += A_b x : later column blocks of a split matrix
+            if constexpr (BCAST) store_bcast(y, peers, r, sum); else y[r] = sum;
+            wrote = true;
+          }
           if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
         }
       }
@@ -306,7 +315,11 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
       if (valid && gl == 0) {
         bool wrote = false;
         if (lo_g < S) { head[t] = sum; wrote = true; }                  // continues an earlier row
-        else if (r < r_last || lo_g < E) { store_bcast(y, peers, r, sum); wrote = true; }  // this tile owns y[r]
+        else if (r < r_last || lo_g < E) {                              // this tile owns y[r]
+          if (accumulate) sum = vadd(sum, y[r]);
+          if constexpr (BCAST) store_bcast(y, peers, r, sum); else y[r] = sum;
+            wrote = true;
+        }
         if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
       }
     }

@@ -172,6 +172,59 @@ class SpmvPlan:
             pass
 
 
+class ColBlock:
+    """Owner of a native b2s_colblock (column-blocked copy of a row block) + its workspace.
+
+    Built when ``suggest`` says the gathers of x have no L2 locality (x much larger than ~40 MB and
+    rows reaching across it); holds a copy of the values, so it is cached with the row block and
+    dropped whenever the matrix data changes."""
+
+    @staticmethod
+    def suggest(vt, it, nrows, ncols, nnz, indptr, indices) -> int:
+        nb = ctypes.c_int(1)
+        N.check(N.load().b2s_csr_colblock_suggest(vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices),
+                                                  stream_ptr(), byref(nb)), "csr_colblock_suggest")
+        return int(nb.value)
+
+    def __init__(self, vt, it, nrows, ncols, nnz, indptr, indices, data, nblocks):
+        lib = N.load()
+        nbytes = int(lib.b2s_csr_colblock_workspace_bytes(vt, it, nrows, nnz, nblocks))
+        if nbytes < 0:
+            raise ValueError("bad colblock arguments")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=indptr.device)
+        self.handle = c_void_p(0)
+        self._lib = lib
+        N.check(lib.b2s_csr_colblock_create(vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(data),
+                                            nblocks, ptr(self.ws), nbytes, stream_ptr(), byref(self.handle)),
+                "csr_colblock_create")
+        self.nblocks = nblocks
+
+    def info(self):
+        nb, bc = ctypes.c_int(0), c_int64(0)
+        per = (c_int64 * 32)()
+        N.check(self._lib.b2s_csr_colblock_info(self.handle, byref(nb), byref(bc), per), "csr_colblock_info")
+        return {"nblocks": nb.value, "block_cols": bc.value, "blk_nnz": [int(per[i]) for i in range(nb.value)]}
+
+    def spmv(self, x, y, w=None, dot_out=None, peer_ptrs=None):
+        arr, npeers = None, 0
+        if peer_ptrs is not None:
+            peer_ptrs, npeers = _npeers(peer_ptrs)
+            arr = _peer_array(peer_ptrs)
+        N.check(self._lib.b2s_spmv_colblock(
+            self.handle, ptr(x), ptr(y), ptr(w) if w is not None else c_void_p(0),
+            ptr(dot_out) if dot_out is not None else c_void_p(0),
+            ctypes.cast(arr, c_void_p) if arr is not None else c_void_p(0), npeers, stream_ptr()),
+            "spmv_colblock")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.b2s_csr_colblock_destroy(self.handle)
+                self.handle = c_void_p(0)
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------ typed wrappers
 def spmv(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan=None, variant=N.B2S_SPMV_AUTO):
     N.check(

@@ -41,6 +41,12 @@ SIGNATURES = {
     "b2s_spmv_csr": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "b2s_spmv_csr_bcast": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     "b2s_spmv_csr_dot": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b2s_csr_colblock_suggest": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, POINTER(c_int)]),
+    "b2s_csr_colblock_workspace_bytes": (_I64, [c_int, c_int, _I64, _I64, c_int]),
+    "b2s_csr_colblock_create": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, c_int, _P, _I64, _P, POINTER(_P)]),
+    "b2s_csr_colblock_destroy": (None, [_P]),
+    "b2s_csr_colblock_info": (c_int, [_P, POINTER(c_int), POINTER(_I64), POINTER(_I64)]),
+    "b2s_spmv_colblock": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P]),
     "b2s_axpby": (c_int, [c_int, _I64, _P, _P, _P, _P, c_int, c_int, _P]),
     "b2s_reduce_workspace_bytes": (_I64, []),
     "b2s_dot": (c_int, [c_int, _I64, _P, _P, c_int, _P, _P, _P]),

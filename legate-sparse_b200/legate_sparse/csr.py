@@ -57,7 +57,7 @@ def _as_host(x, dtype=None, copy=False):
 class _RowBlock:
     """Device-resident rows [r0, r1) of a matrix: rebased indptr, (narrowed) indices, data."""
 
-    __slots__ = ("r0", "r1", "nnz", "indptr", "indices", "data", "itype", "plan", "_colrange")
+    __slots__ = ("r0", "r1", "nnz", "indptr", "indices", "data", "itype", "plan", "colblock", "_colrange")
 
     def __init__(self, r0, r1, indptr, indices, data):
         self.r0, self.r1 = int(r0), int(r1)
@@ -65,6 +65,7 @@ class _RowBlock:
         self.nnz = int(data.numel())
         self.itype = N.B2S_I32 if indices.dtype == torch.int32 else N.B2S_I64
         self.plan = None
+        self.colblock = None   # None: not decided yet, False: not worthwhile, else _device.ColBlock
         self._colrange = None
 
     @property
@@ -340,6 +341,21 @@ class csr_array(CompressedBase):
 
             blk.plan = SpmvPlan(blk.itype, blk.nrows, self.shape[1], blk.nnz, blk.indptr, blk.indices)
         return blk.plan
+
+    def _colblock(self, blk: _RowBlock):
+        """Column-blocked copy of the row block when x would not stay L2-resident (decided once by the
+        native heuristic; see b2s_csr_colblock_suggest), else None."""
+        if blk.colblock is None:
+            blk.colblock = False
+            if blk.nnz > 0 and settings.spmv_variant() == N.B2S_SPMV_AUTO:
+                from ._device import ColBlock, vt_enum
+
+                vt = vt_enum(self.dtype)
+                nb = ColBlock.suggest(vt, blk.itype, blk.nrows, self.shape[1], blk.nnz, blk.indptr, blk.indices)
+                if nb > 1:
+                    blk.colblock = ColBlock(vt, blk.itype, blk.nrows, self.shape[1], blk.nnz, blk.indptr,
+                                            blk.indices, blk.data, nb)
+        return blk.colblock or None
 
     # ------------------------------------------------------------------ properties
     @property
@@ -673,6 +689,10 @@ def _spmv_block(A: csr_array, blk: _RowBlock, x_dev, y_dev):
     """y_dev[0:blk.nrows] = A[blk.r0:blk.r1, :] @ x_dev   (one native launch sequence)."""
     from ._device import spmv as _spmv, vt_enum
 
+    cb = A._colblock(blk)
+    if cb is not None:
+        cb.spmv(x_dev, y_dev)
+        return
     plan = A._plan(blk)
     _spmv(vt_enum(A.dtype), blk.itype, blk.nrows, A.shape[1], blk.nnz, blk.indptr, blk.indices, blk.data,
           x_dev, y_dev, plan=plan, variant=settings.spmv_variant())
@@ -714,7 +734,9 @@ def spmv(A: csr_array, x, y=None):
 
             sv.barrier()   # peers are done reading the previous content
             local = sv.t[blk.r0 : blk.r1]
-            if blk.nnz > 0 and _bcast_ok(blk):
+            if blk.nnz > 0 and A._colblock(blk) is not None:
+                A._colblock(blk).spmv(x_dev, local, peer_ptrs=sv.peer_ptrs(blk.r0))
+            elif blk.nnz > 0 and _bcast_ok(blk):
                 spmv_bcast(vt_enum(A.dtype), blk.itype, blk.nrows, A.shape[1], blk.nnz, blk.indptr,
                            blk.indices, blk.data, x_dev, local, sv.peer_ptrs(blk.r0), A._plan(blk))
             else:

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../include/b200sparse.h"
@@ -96,6 +98,41 @@ double run_case(const char* name, b2s_itype it, int64_t n, int64_t m, int64_t nn
                 const I* cols, const double* vals, const double* x, double* y, int variant, int tile, int iters,
                 bool nowin) {
   if (tile) { char buf[32]; snprintf(buf, sizeof buf, "%d", tile); setenv("B2S_SPMV_TILE_NNZ", buf, 1); }
+  if (getenv("SWEEP_COLBLOCK")) {   // column-blocked operand: SWEEP_COLBLOCK=N blocks (0 = library heuristic)
+    int nb = atoi(getenv("SWEEP_COLBLOCK"));
+    if (nb == 0) {
+      if (b2s_csr_colblock_suggest(B2S_F64, it, n, m, nnz, indptr, cols, nullptr, &nb)) { printf("suggest failed\n"); exit(1); }
+      printf("suggested blocks: %d\n", nb);
+      if (nb < 2) return 0;
+    }
+    int64_t wb = b2s_csr_colblock_workspace_bytes(B2S_F64, it, n, nnz, nb);
+    void* ws = nullptr; CK(cudaMalloc(&ws, wb));
+    b2s_colblock* cb = nullptr;
+    Timer tc; tc.start();
+    if (b2s_csr_colblock_create(B2S_F64, it, n, m, nnz, indptr, cols, vals, nb, ws, wb, nullptr, &cb)) {
+      printf("colblock_create failed: %s\n", b2s_last_error_string()); exit(1);
+    }
+    float cms = tc.stop();
+    for (int i = 0; i < 3; ++i)
+      if (b2s_spmv_colblock(cb, x, y, nullptr, nullptr, nullptr, 0, nullptr)) { printf("spmv failed: %s\n", b2s_last_error_string()); exit(1); }
+    CK(cudaDeviceSynchronize());
+    Timer t; t.start();
+    for (int i = 0; i < iters; ++i) b2s_spmv_colblock(cb, x, y, nullptr, nullptr, nullptr, 0, nullptr);
+    float ms = t.stop() / iters;
+    double bytes = (double)nnz * (8 + sizeof(I)) + (double)(n + 1) * 8 + (double)m * 8 + (double)n * 8;
+    printf("%-22s colblock=%d (build %.1f ms) idx%zu : %8.3f ms  %8.1f GFLOP/s  %7.1f GB/s (algorithmic)\n", name, nb, cms,
+           sizeof(I) * 8, ms, 2.0 * nnz / ms / 1e6, bytes / ms / 1e6);
+    // cross-check against the plain path
+    double* y2; CK(cudaMalloc(&y2, n * 8));
+    if (b2s_spmv_csr(B2S_F64, it, n, m, nnz, indptr, cols, vals, x, y2, nullptr, B2S_SPMV_ROWVEC, nullptr)) { printf("ref spmv failed\n"); exit(1); }
+    std::vector<double> a(1 << 16), b(1 << 16);
+    CK(cudaMemcpy(a.data(), y, a.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), y2, b.size() * 8, cudaMemcpyDeviceToHost));
+    double md = 0; for (size_t i = 0; i < a.size() && (int64_t)i < n; ++i) md = std::max(md, std::abs(a[i] - b[i]));
+    printf("  max |colblock - rowvec| over first rows: %.3e\n", md);
+    cudaFree(y2); b2s_csr_colblock_destroy(cb); cudaFree(ws);
+    return ms;
+  }
   if (nowin) setenv("B2S_SPMV_NO_WINDOW", "1", 1); else unsetenv("B2S_SPMV_NO_WINDOW");
   b2s_spmv_plan* plan = nullptr;
   void* ws = nullptr;
@@ -129,7 +166,7 @@ int main(int argc, char** argv) {
   int k = argc > 2 ? atoi(argv[2]) : 50;
   int iters = argc > 3 ? atoi(argv[3]) : 20;
   std::string mode = argc > 4 ? argv[4] : "random";
-  int64_t m = n;
+  int64_t m = getenv("SWEEP_NCOLS") ? atoll(getenv("SWEEP_NCOLS")) : n;  // rectangular: one column block
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   if (getenv("SWEEP_L2_PERSIST")) {
     size_t want = (size_t)atoll(getenv("SWEEP_L2_PERSIST")) << 20;
