@@ -39,6 +39,14 @@ def main():
     assert blk.nrows == dist.row_block_bounds(n, G)[rank + 1] - dist.row_block_bounds(n, G)[rank]
     yl = A.dot_local(torch.from_numpy(x).cuda())
     assert relerr(yl.cpu().numpy(), (S @ x)[blk.r0 : blk.r1]) < 1e-12
+    # column-blocked operand + fused all-gather: the last block's launch does the peer stores
+    os.environ["B2S_SPMV_COLBLOCK"] = "3"
+    Ab = sparse.csr_array(S)
+    yb = Ab @ x
+    assert Ab._block().colblock not in (None, False)
+    assert relerr(yb, S @ x) < 1e-12
+    assert relerr(Ab @ (2.0 * x), 2.0 * (S @ x)) < 1e-12   # second call: buffers reused after the barrier
+    os.environ.pop("B2S_SPMV_COLBLOCK")
     # nnz-balanced partition on a power-law matrix
     d, c, p = gen.powerlaw_csr(8000, 8000, max_row=4000, seed=7)
     Sp = sp.csr_array((d, c, p), shape=(8000, 8000))

@@ -8,7 +8,7 @@ mkdir -p gpurun_out /tmp/ncu
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
    python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/launches_bench.log 2>&1
 # top kernel, full set, inside the bench command
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_pipe -s 3 -c 1 -f -o /tmp/ncu/spmv_bench \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_pipe -s 4 -c 2 -f -o /tmp/ncu/spmv_bench \
    python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/ncu_bench.log 2>&1
 ncu -i /tmp/ncu/spmv_bench.ncu-rep --page raw --csv > gpurun_out/ncu_spmv_bench_raw.csv 2>/dev/null
 ncu -i /tmp/ncu/spmv_bench.ncu-rep --page details --csv > gpurun_out/ncu_spmv_bench_details.csv 2>/dev/null
