@@ -152,6 +152,11 @@ int b2s_csr_colblock_info(const b2s_colblock* cb, int* nblocks, int64_t* block_c
  * broadcast (y_peers, npeers as in b2s_spmv_csr_bcast) are applied by the last block's launch. */
 int b2s_spmv_colblock(const b2s_colblock* cb, const void* x, void* y, const void* w, void* dot_out,
                       void* const* y_peers, int npeers, b2s_stream_t stream);
+/* Block `block` of that sequence only (call for 0..nblocks-1 in order).  Block b reads only
+ * x[b*block_cols, (b+1)*block_cols), so a host caller can overlap the H2D copy of the next slice
+ * of x with this launch. */
+int b2s_spmv_colblock_part(const b2s_colblock* cb, int block, const void* x, void* y,
+                           b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Dense vector kernels of the CG/GMRES loop.

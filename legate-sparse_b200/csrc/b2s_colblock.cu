@@ -341,3 +341,19 @@ extern "C" int b2s_spmv_colblock(const b2s_colblock* cb, const void* x, void* y,
   }
   return B2S_OK;
 }
+
+// One block of the sequence above (block `b` only): lets the caller overlap the host->device copy
+// of x slice b+1 with the launch of block b (the slice [b*block_cols, (b+1)*block_cols) of x is
+// all that block b reads).  Call for b = 0..nblocks-1 in order.
+extern "C" int b2s_spmv_colblock_part(const b2s_colblock* cb, int block, const void* x, void* y,
+                                      b2s_stream_t stream) {
+  B2S_REQUIRE(cb != nullptr, "colblock is null");
+  B2S_REQUIRE(block >= 0 && block < cb->nblocks, "block out of range");
+  B2S_REQUIRE(x != nullptr && y != nullptr, "null vector");
+  if (cb->blk_nnz[block] == 0) return B2S_OK;
+  int first = 0;
+  while (cb->blk_nnz[first] == 0) ++first;
+  return spmv_entry(cb->vt, cb->it, cb->nrows, cb->ncols, cb->blk_nnz[block], cb->indptr[block],
+                    cb->cols[block], cb->vals[block], x, y, cb->plan[block], B2S_SPMV_PIPE, nullptr,
+                    nullptr, nullptr, nullptr, 0, block != first, stream);
+}

@@ -172,6 +172,17 @@ class SpmvPlan:
             pass
 
 
+_side = {}
+
+
+def _side_stream():
+    """one extra stream per device for copies that overlap kernels"""
+    d = torch.cuda.current_device()
+    if d not in _side:
+        _side[d] = torch.cuda.Stream(device=d)
+    return _side[d]
+
+
 class ColBlock:
     """Owner of a native b2s_colblock (column-blocked copy of a row block) + its workspace.
 
@@ -215,6 +226,28 @@ class ColBlock:
             ptr(dot_out) if dot_out is not None else c_void_p(0),
             ctypes.cast(arr, c_void_p) if arr is not None else c_void_p(0), npeers, stream_ptr()),
             "spmv_colblock")
+
+    def spmv_from_host(self, x_host: torch.Tensor, y, ncols):
+        """y = A x with x in host memory: slice b+1 of x is copied on a side stream while block b
+        runs (block b only reads its own slice of x).  Returns the device copy of x."""
+        info = self.info()
+        bw, nb = info["block_cols"], info["nblocks"]
+        x_dev = torch.empty(ncols, dtype=x_host.dtype, device=y.device)
+        cur = torch.cuda.current_stream()
+        side = _side_stream()
+        side.wait_stream(cur)
+        for b in range(nb):
+            lo, hi = b * bw, min((b + 1) * bw, ncols)
+            if hi > lo:
+                with torch.cuda.stream(side):
+                    x_dev[lo:hi].copy_(x_host[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                cur.wait_event(ev)
+            N.check(self._lib.b2s_spmv_colblock_part(self.handle, b, ptr(x_dev), ptr(y), stream_ptr()),
+                    "spmv_colblock_part")
+        x_dev.record_stream(side)
+        return x_dev
 
     def __del__(self):
         try:

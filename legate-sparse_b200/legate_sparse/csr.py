@@ -713,16 +713,29 @@ def spmv(A: csr_array, x, y=None):
 
     blk = A._block()
     host_io = not _is_dev(x)
-    x_dev = to_device(x, dtype=A.dtype)
     G = dist.world_size()
     n = A.shape[0]
-    if G == 1:
+    piped = False
+    if G == 1 and host_io and A._colblock(blk) is not None:
+        # host x + column-blocked operand: copy slice b+1 of x while block b runs
+        from ._device import torch_dtype
+
+        xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(numpy.ascontiguousarray(x))
+        if xh.dtype == torch_dtype(A.dtype) and xh.dim() == 1 and xh.is_contiguous():
+            y_dev = y if (y is not None and _is_dev(y) and y.is_contiguous()) else empty(n, A.dtype)
+            A._colblock(blk).spmv_from_host(xh, y_dev, A.shape[1])
+            piped = True
+    if piped:
+        pass
+    elif G == 1:
+        x_dev = to_device(x, dtype=A.dtype)
         if y is not None and _is_dev(y) and y.is_contiguous():
             y_dev = y
         else:
             y_dev = empty(n, A.dtype)
         _spmv_block(A, blk, x_dev, y_dev)
     else:
+        x_dev = to_device(x, dtype=A.dtype)
         bounds = A.row_bounds()
         from ._device import torch_dtype
 

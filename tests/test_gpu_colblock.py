@@ -165,6 +165,17 @@ def test_csr_array_uses_colblock_when_forced(monkeypatch):
     assert A._block().colblock not in (None, False)
     assert A._block().colblock.info()["nblocks"] == 4
     assert np.allclose(y, S @ x, rtol=1e-12, atol=1e-12)
+    # pinned host tensors in/out (bench e2e path): x slices are copied while earlier blocks run
+    import torch
+
+    xh = torch.from_numpy(x).pin_memory()
+    yh = torch.empty(5000, dtype=torch.float64).pin_memory()
+    A.dot(xh, out=yh)
+    torch.cuda.synchronize()
+    assert np.allclose(yh.numpy(), S @ x, rtol=1e-12, atol=1e-12)
+    # device tensors stay on the device
+    yd = A @ torch.from_numpy(x).cuda()
+    assert yd.is_cuda and np.allclose(yd.cpu().numpy(), S @ x, rtol=1e-12, atol=1e-12)
     A.data = S.data * 3.0
     assert np.allclose(A @ x, 3.0 * (S @ x), rtol=1e-12, atol=1e-12)
     monkeypatch.setenv("B2S_SPMV_COLBLOCK", "0")
