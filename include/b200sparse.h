@@ -71,10 +71,11 @@ int64_t     b2s_launch_count(void);
  * ---------------------------------------------------------------------- */
 typedef struct b2s_spmv_plan b2s_spmv_plan; /* opaque, host object */
 
-/* AUTO: MERGE when a plan is given and the arrays are 16-byte aligned, else TILE, else ROWVEC.
- * MERGE  = persistent kernel, (col,val,indptr[,x window]) streamed by TMA bulk copies into a shared-
- *          memory ring by a producer warp; consumers are nnz-balanced per lane + warp segmented scan
- * PIPE   = same TMA ring, consumers walk one row per lane group (kept for A/B measurements)
+/* AUTO: PIPE when a plan is given and the arrays are 16-byte aligned, else TILE, else ROWVEC.
+ * PIPE   = persistent kernel, (col,val,indptr[,x window]) streamed by TMA bulk copies into a shared-
+ *          memory ring by a producer warp; consumers: row-walk (window matrices) or products+row
+ *          reduction (x gathered from L2)
+ * MERGE  = same TMA ring, consumers nnz-balanced per lane + warp segmented scan (kept for A/B)
  * TILE   = one CTA per tile, register-staged 128-bit loads (fallback for unaligned slices)
  * ROWVEC = plan-free 2..32 lanes per row */
 enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2, B2S_SPMV_PIPE = 3, B2S_SPMV_MERGE = 4,
