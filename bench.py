@@ -121,6 +121,8 @@ class Clocks:
         self.index = index
 
     def start(self):
+        if os.environ.get("B2S_BENCH_NO_CLOCKS"):   # A/B switch: does the 10 Hz nvidia-smi poll perturb a leg?
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",

@@ -199,6 +199,25 @@ int b2s_cg_pupdate_halo(b2s_dtype vt, int64_t n, void* p, const void* r, const v
                         const int64_t* hi, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Restarted GMRES, classical Gram-Schmidt (legate_sparse/linalg.py:607-640,655-657): the
+ * tall-skinny products  h = V^H u,  u -= V h,  ||u||,  v = u/||u||,  x += V y  that upstream are
+ * cupynumeric GEMVs on an (n, restart) array.  The Krylov basis is stored basis-vector-major:
+ * vector c is basis[c*ldv .. c*ldv+n), ldv >= n (ldv*sizeof(value) a multiple of 16 enables the
+ * 128-bit path).  `workspace`: b2s_cgs_workspace_bytes() bytes, zero-initialised once, reusable.
+ * ------------------------------------------------------------------------ */
+int64_t b2s_cgs_workspace_bytes(void);
+/* h[c] = sum_i conj(basis[c][i]) * u[i],  c < k   (device output, k values) */
+int b2s_cgs_project(b2s_dtype vt, int64_t n, int k, const void* basis, int64_t ldv, const void* u,
+                    void* h, void* workspace, b2s_stream_t stream);
+/* u[i] += s * sum_c h[c] * basis[c][i]  with s = -1 if negate else +1 (k <= 1024);
+ * nrm_out (optional, device REAL scalar) = ||u_new||_2 in the same pass. */
+int b2s_cgs_update(b2s_dtype vt, int64_t n, int k, const void* basis, int64_t ldv, const void* h,
+                   int negate, void* u, void* nrm_out, void* workspace, b2s_stream_t stream);
+/* out[i] = x[i] / s[0]   (s: device REAL scalar; out may be a basis row) */
+int b2s_vscale_inv(b2s_dtype vt, int64_t n, const void* x, const void* s, void* out,
+                   b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * CSR x CSR SpGEMM  C = A B.   replaces SpGEMMCSRxCSRxCSRGPU
  *   src/sparse/array/csr/spgemm_csr_csr_csr.cu:64-487 (cuSPARSE SpGEMM) and the
  *   two-task CPU shape (NNZ task + numeric task, csr.py:687-744,

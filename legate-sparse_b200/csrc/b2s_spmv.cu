@@ -354,9 +354,19 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   static int blocks_per_sm = -1;  // per instantiation
   if (blocks_per_sm < 0) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Every x gather in flight holds an L1 line, so the gather-bound products kernel wants L1, not
+    // shared memory: on 2048-nnz tiles (57.6 KB per CTA) two CTAs with the 132 KB shared-memory
+    // configuration (L1 = 124 KB) beat the three CTAs the occupancy API offers (196 KB, L1 = 60 KB):
+    // 2.30 vs 2.375 ms on the column-blocked C2 matrix; a 228 KB carve-out costs 65 %
+    // (tools/gpu_occ.sh).  B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
+    int carve = (!WINDOW && IPT == 8) ? 55 : -1, cap = (!WINDOW && IPT == 8) ? 2 : 0;
+    if (const char* e = getenv("B2S_SPMV_CARVEOUT")) carve = atoi(e);
+    if (const char* e = getenv("B2S_SPMV_CTAS")) cap = atoi(e);
+    if (carve >= 0) B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     int nb = 0;
     B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
     if (nb < 1) { set_error("spmv_pipe_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
+    if (cap >= 1 && cap < nb) nb = cap;
     blocks_per_sm = nb;
   }
   int64_t grid = (int64_t)blocks_per_sm * num_sms();

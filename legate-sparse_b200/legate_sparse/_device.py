@@ -359,6 +359,43 @@ def nrm2(x, out=None):
     return out
 
 
+_cgs_ws = {}
+
+
+def cgs_ws() -> torch.Tensor:
+    dev = require_cuda()
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _cgs_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(int(N.load().b2s_cgs_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _cgs_ws[key] = ws
+    return ws
+
+
+def cgs_project(basis, ldv, n, k, u, h):
+    """h[:k] = basis[:k, :n]^H u   (GMRES Arnoldi projection; basis rows are the Krylov vectors)"""
+    dt = np_dtype_of(u)
+    N.check(N.load().b2s_cgs_project(vt_enum(dt), n, k, ptr(basis), ldv, ptr(u), ptr(h), ptr(cgs_ws()),
+                                     stream_ptr()), "cgs_project")
+    return h
+
+
+def cgs_update(basis, ldv, n, k, h, u, negate=True, nrm_out=None):
+    """u -= basis[:k]^T h (negate) or u += ... ; optional fused ||u|| into the device scalar nrm_out"""
+    dt = np_dtype_of(u)
+    N.check(N.load().b2s_cgs_update(vt_enum(dt), n, k, ptr(basis), ldv, ptr(h), int(bool(negate)), ptr(u),
+                                    ptr(nrm_out) if nrm_out is not None else c_void_p(0), ptr(cgs_ws()),
+                                    stream_ptr()), "cgs_update")
+    return u
+
+
+def vscale_inv(x, s, out):
+    """out = x / s[0] with s a device real scalar"""
+    dt = np_dtype_of(x)
+    N.check(N.load().b2s_vscale_inv(vt_enum(dt), x.numel(), ptr(x), ptr(s), ptr(out), stream_ptr()), "vscale_inv")
+    return out
+
+
 def cg_update(x, r, p, q, rho, pq, rr_out):
     dt = np_dtype_of(x)
     N.check(

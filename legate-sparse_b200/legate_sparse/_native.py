@@ -48,6 +48,10 @@ SIGNATURES = {
     "b2s_csr_colblock_info": (c_int, [_P, POINTER(c_int), POINTER(_I64), POINTER(_I64)]),
     "b2s_spmv_colblock": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P]),
     "b2s_spmv_colblock_part": (c_int, [_P, c_int, _P, _P, _P]),
+    "b2s_cgs_workspace_bytes": (_I64, []),
+    "b2s_cgs_project": (c_int, [c_int, _I64, c_int, _P, _I64, _P, _P, _P, _P]),
+    "b2s_cgs_update": (c_int, [c_int, _I64, c_int, _P, _I64, _P, c_int, _P, _P, _P, _P]),
+    "b2s_vscale_inv": (c_int, [c_int, _I64, _P, _P, _P, _P]),
     "b2s_axpby": (c_int, [c_int, _I64, _P, _P, _P, _P, c_int, c_int, _P]),
     "b2s_reduce_workspace_bytes": (_I64, []),
     "b2s_dot": (c_int, [c_int, _I64, _P, _P, c_int, _P, _P, _P]),

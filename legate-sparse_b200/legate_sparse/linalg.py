@@ -519,8 +519,9 @@ def gmres(
     rtol=1e-5,
 ):
     """Restarted GMRES with classical Gram-Schmidt (reference linalg.py:540-668, itself the
-    CuPy algorithm).  Returns ``(x, info)``.  SpMV and norms run on the B200 kernels; the
-    tall-skinny ``V^H u`` / ``V y`` products are library GEMVs on the device and the
+    CuPy algorithm).  Returns ``(x, info)``.  SpMV, norms and the tall-skinny
+    ``V^H u`` / ``u -= V h`` / ``x += V y`` products run on the B200 kernels (b2s_cgs_project /
+    b2s_cgs_update / b2s_vscale_inv; the basis is stored basis-vector-major); the
     (restart+1) x restart least-squares problem is solved on the host, as upstream."""
     from . import _device as D
 
@@ -560,42 +561,50 @@ def gmres(
         callback_type = None
 
     dev = b_dev.device
-    V = torch.empty((n, restart), dtype=tdt, device=dev)
+    # Krylov basis, basis-vector-major (row c = v_c): every kernel streams unit-stride rows.
+    # The leading dimension is padded so that each row starts 16-byte aligned (128-bit loads).
+    ldv = (n + 31) // 32 * 32
+    V = torch.empty((restart, ldv), dtype=tdt, device=dev)
     H = torch.zeros((restart + 1, restart), dtype=tdt, device=dev)
+    hcol = torch.empty(restart, dtype=tdt, device=dev)
+    hn = torch.empty(1, dtype=D.torch_dtype(D.real_dtype(dtype)), device=dev)
     e = np.zeros((restart + 1,), dtype=dtype)
 
     iters = 0
     while True:
         mx = Md.apply(x)
         r = b_dev - Ad.apply(mx)
-        r_norm = float(D.nrm2(r).item())
+        D.nrm2(r, out=hn)
+        r_norm = float(hn.item())
         if callback_type == "x":
             callback(D.to_host(mx) if numpy_mode else mx)
         elif callback_type == "pr_norm" and iters > 0:
             callback(r_norm / b_norm)
         if r_norm <= atol or iters >= maxiter:
             break
-        v = r / r_norm
-        V[:, 0] = v
+        D.vscale_inv(r, hn, V[0, :n])          # v_0 = r / ||r||
         e[0] = r_norm
 
-        # Arnoldi iteration
+        # Arnoldi iteration (classical Gram-Schmidt, reference linalg.py:627-657)
         for j in range(restart):
-            z = Md.apply(v)
+            vj = V[j, :n]
+            z = vj if Md.is_identity else Md.apply(vj)     # operators never write their input
             u = Ad.apply(z)
-            Vj = V[:, : j + 1]
-            h = Vj.conj().T @ u
-            u = u - Vj @ h
-            H[: j + 1, j] = h
-            hn = D.nrm2(u)
+            if u.dtype != tdt:
+                u = u.to(tdt)
+            if u.data_ptr() == vj.data_ptr() or not u.is_contiguous():
+                u = u.contiguous().clone()      # never update a basis row in place
+            D.cgs_project(V, ldv, n, j + 1, u, hcol)        # h = V_j^H u
+            D.cgs_update(V, ldv, n, j + 1, hcol, u, negate=True, nrm_out=hn)   # u -= V_j h ; hn = ||u||
+            H[: j + 1, j] = hcol[: j + 1]
             H[j + 1, j] = hn[0]
             if j + 1 < restart:
-                v = u / hn[0]
-                V[:, j + 1] = v
+                D.vscale_inv(u, hn, V[j + 1, :n])          # v_{j+1} = u / ||u||
 
-        # least squares H y = e on the host (small)
+        # least squares H y = e on the host (small), as upstream (linalg.py:658-661)
         y = np.linalg.lstsq(D.to_host(H), e, rcond=None)[0]
-        x = x + V @ D.to_device(np.ascontiguousarray(y), dtype=dtype)
+        y_dev = D.to_device(np.ascontiguousarray(y), dtype=dtype)
+        D.cgs_update(V, ldv, n, restart, y_dev, x, negate=False)   # x += V y
         iters += restart
 
     info = 0

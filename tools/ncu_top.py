@@ -12,6 +12,7 @@ def main(path, top=25):
     mix = {h: 0 for h in stalls}
     for r in rows[2:]:
         if len(r) < len(hdr): continue
+        if r[s_all] == hdr[s_all]: break   # a second captured launch starts here: report the first only
         n = int(float(r[s_all] or 0))
         tot += n
         for h in stalls: mix[h] += int(float(r[ix[h]] or 0))

@@ -2,7 +2,8 @@
 """Secondary measurements (not the bench.py headline): CG iterations/s on the 5-point Laplacian
 (BASELINE config 3) and SpGEMM A@A on banded / R-MAT matrices (config 4), single GPU or torchrun.
 
-    python tools/side_bench.py cg [--grid 4096] [--iters 200]
+    python tools/side_bench.py cg [--grid 4096] [--iters 200] [--no-solve]
+    python tools/side_bench.py gmres [--grid 4096] [--iters 100]
     python tools/side_bench.py spgemm [--scale 20] [--banded-n 4000000]
 Prints one JSON object per measurement.
 """
@@ -97,14 +98,49 @@ def run_cg(args):
                      "ref_algorithm_gbs": (B + 120 * n) * it / dt / 1e9}
     os.environ["LEGATE_SPARSE_CG_UNFUSED"] = "0"
     # convergence run
-    t0 = time.perf_counter()
-    x, it = linalg.cg(A, b, rtol=1e-10, maxiter=20000)
-    torch.cuda.synchronize()
-    out["solve_rtol_1e-10"] = {"iters": it, "seconds": time.perf_counter() - t0,
-                               "rel_residual": float((torch.linalg.vector_norm(b - (A @ x)) /
-                                                      torch.linalg.vector_norm(b)).item())}
+    if not args.no_solve:
+        t0 = time.perf_counter()
+        x, it = linalg.cg(A, b, rtol=1e-10, maxiter=20000)
+        torch.cuda.synchronize()
+        out["solve_rtol_1e-10"] = {"iters": it, "seconds": time.perf_counter() - t0,
+                                   "rel_residual": float((torch.linalg.vector_norm(b - (A @ x)) /
+                                                          torch.linalg.vector_norm(b)).item())}
     if rank == 0:
         print(json.dumps(out))
+    dist.shutdown()
+
+
+def run_gmres(args):
+    """restarted GMRES (restart 20) on the 5-point Laplacian: time per restart cycle and the HBM
+    rate of its streams (SpMV B + CGS project (k+1)n + update (k+2)n + scale 2n values, k = 1..20)."""
+    dist.init()
+    G, rank = dist.world_size(), dist.rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    N = args.grid
+    n = N * N
+    bounds = dist.row_block_bounds(n, G)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    data, idx, ptr = poisson2d_block(N, r0, r1, dev)
+    A = sparse.csr_array.from_row_block(data, idx, ptr, (n, n), row_start=r0, bounds=bounds)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    b = torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    nnz = A.nnz
+    restart, cycles = 20, args.iters // 20 if args.iters >= 20 else 5
+    linalg.gmres(A, b, rtol=0.0, atol=0.0, restart=restart, maxiter=restart)   # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, info = linalg.gmres(A, b, rtol=0.0, atol=0.0, restart=restart, maxiter=restart * cycles)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    B = nnz * 12 + (n + 1) * 8 + 16 * n
+    per_cycle = restart * B + sum((2 * k + 5) for k in range(1, restart + 1)) * 8 * n + (restart + 2) * 8 * n + B + 24 * n
+    res = float((torch.linalg.vector_norm(b - (A @ x)) / torch.linalg.vector_norm(b)).item())
+    if rank == 0:
+        print(json.dumps({"what": f"GMRES(20) on the 5-point Laplacian {N}x{N} (n={n}), fp64, {cycles} restart cycles",
+                          "n_gpus": G, "ms_per_cycle": dt / cycles * 1e3, "iters_per_s": restart * cycles / dt,
+                          "stream_bytes_per_cycle": per_cycle, "stream_gbs": per_cycle * cycles / dt / 1e9,
+                          "rel_residual_after": res}))
     dist.shutdown()
 
 
@@ -267,7 +303,8 @@ def run_powerlaw(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["cg", "spgemm", "powerlaw"])
+    ap.add_argument("which", choices=["cg", "gmres", "spgemm", "powerlaw"])
+    ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--pl-rows", type=int, default=8_000_000)
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--iters", type=int, default=200)
@@ -275,4 +312,4 @@ if __name__ == "__main__":
     ap.add_argument("--verify-scale", type=int, default=16)
     ap.add_argument("--banded-n", type=int, default=4_000_000)
     a = ap.parse_args()
-    {"cg": run_cg, "spgemm": run_spgemm, "powerlaw": run_powerlaw}[a.which](a)
+    {"cg": run_cg, "gmres": run_gmres, "spgemm": run_spgemm, "powerlaw": run_powerlaw}[a.which](a)
