@@ -11,7 +11,10 @@ y = A x over the whole matrix.  The matrix is synthetic and generated on the dev
 counter-based hash, so every N sees the SAME matrix.
 
 One JSON line is printed by rank 0.  Keys beyond the base contract:
-  roofline      HBM roofline of the SpMV launch sequence (tile kernel + its fix-up kernel)
+  roofline      HBM roofline of the SpMV launch sequence (pipe kernel + its fix-up kernel, once per
+                column block: the library splits this matrix into 2 column blocks so that the
+                gathered slice of x stays L2 resident); achieved = plain-CSR algorithmic bytes / time
+  cg            CG iterations/s on the 5-point Laplacian 4096^2 (the second half of the metric)
   cpu_baseline  the oracle's OpenMP restatement of the reference CPU task (spmv_omp.cc:36-44)
                 timed on the host cores on a bounded row sample of the same matrix
   banded        same measurement on the reference's own microbenchmark generator

@@ -161,6 +161,16 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
       const int64_t S = t * (int64_t)T;
       const int64_t E = min(S + (int64_t)T, nnz);
       const bool use_win = WINDOW && meta.win_staged;
+      const int64_t r_begin = meta.r_begin, r_last = meta.r_last;
+      const int64_t nr = r_last - r_begin + 1;
+      int lanes = 1;
+      while (lanes < 32 && (int64_t)(lanes * 2) * nr <= kPipeConsumers) lanes <<= 1;
+      const int groups = kPipeConsumers / lanes;
+      const int gl = tid & (lanes - 1);
+      // y += A_b x: fetch the old y of this thread's first row now, so that its latency hides
+      // behind the gathers instead of sitting in front of the store
+      V ypre = zero_of<V>();
+      if (accumulate && gl == 0 && tid / lanes < nr && r_begin + tid / lanes < nrows) ypre = y[r_begin + tid / lanes];
       if (meta.full_tile) {
 #pragma unroll
         for (int g = 0; g < IPT / 4; ++g) {
@@ -188,12 +198,6 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         }
       }
       consumer_bar_sync();
-      const int64_t r_begin = meta.r_begin, r_last = meta.r_last;
-      const int64_t nr = r_last - r_begin + 1;
-      int lanes = 1;
-      while (lanes < 32 && (int64_t)(lanes * 2) * nr <= kPipeConsumers) lanes <<= 1;
-      const int groups = kPipeConsumers / lanes;
-      const int gl = tid & (lanes - 1);
       for (int64_t base = 0; base < nr; base += groups) {
         const int64_t r = r_begin + base + tid / lanes;
         const bool valid = (base + tid / lanes < nr) && (r < nrows);
@@ -216,7 +220,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           bool wrote = false;
           if (lo_g < S) { head[t] = sum; wrote = true; }
           else if (r < r_last || lo_g < E) {
-            if (accumulate) sum = vadd(sum, y[r]);   // y += A_b x : later column blocks of a split matrix
+            if (accumulate) sum = vadd(sum, base == 0 ? ypre : y[r]);   // y += A_b x : later column blocks
             if constexpr (BCAST) store_bcast(y, peers, r, sum); else y[r] = sum;
             wrote = true;
           }
