@@ -73,13 +73,12 @@ typedef struct b2s_spmv_plan b2s_spmv_plan; /* opaque, host object */
 
 /* AUTO: PIPE when a plan is given and the arrays are 16-byte aligned, else TILE, else ROWVEC.
  * PIPE   = persistent kernel, (col,val,indptr[,x window]) streamed by TMA bulk copies into a shared-
- *          memory ring by a producer warp; consumers: row-walk (window matrices) or products+row
- *          reduction (x gathered from L2)
- * MERGE  = same TMA ring, consumers nnz-balanced per lane + warp segmented scan (kept for A/B)
+ *          memory ring by a producer warp; consumers: row-walk (window matrices) or two ping-pong
+ *          groups doing products + row reduction (x gathered from L2).  nnz-balanced tiles, rows
+ *          that straddle tiles are completed by a fix-up pass (merge-path style decomposition).
  * TILE   = one CTA per tile, register-staged 128-bit loads (fallback for unaligned slices)
  * ROWVEC = plan-free 2..32 lanes per row */
-enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2, B2S_SPMV_PIPE = 3, B2S_SPMV_MERGE = 4,
-       B2S_SPMV_WPIPE = 5 /* TMA ring + warp-autonomous consumers (no CTA barrier), 1024-nnz plans */ };
+enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2, B2S_SPMV_PIPE = 3 };
 
 /* bytes of device workspace a plan for this matrix needs */
 int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz);
@@ -124,8 +123,9 @@ int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, i
 /* ------------------------------------------------------------------------
  * Column-blocked operand for SpMV when x does not stay L2-resident (ncols * sizeof(value) well
  * above ~40 MB and rows that reach across all of x — the random C2 matrix of BASELINE.json).
- * Same role as the cuSPARSE preprocess/buffer step of the reference's SpMV task
- * (src/legate_sparse/array/csr/spmv.cu:27-75): a one-time layout, cached next to the plan.
+ * A one-time layout of the operand of the reference's SpMV task body
+ * (src/sparse/array/csr/spmv.cu:30-163, which only sizes a cuSPARSE buffer —
+ * cusparseSpMV_bufferSize, spmv.cu:117-135 — and has no operand preparation), cached next to the plan.
  * A = [A_0 | A_1 | ...] by column ranges of `block_cols`; y = A_0 x; y += A_1 x; ... — one pipe
  * kernel launch per block, each gathering from one slice of x.  The object keeps device
  * pointers into `workspace` (caller-owned, must outlive it) and a COPY of the values: rebuild it
@@ -262,6 +262,46 @@ int b2s_cast_i32_to_i64(int64_t n, const int32_t* src, int64_t* dst, b2s_stream_
 int b2s_csr_to_dense(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols,
                      const int64_t* indptr, const void* indices, const void* data, void* out,
                      b2s_stream_t stream);
+
+
+/* ------------------------------------------------------------------------
+ * Device-side constructors and the random generator north_star names.
+ * Two-pass shape like the reference's count + fill tasks: the count pass writes per-row counts
+ * into indptr[1..nrows] (pass `indptr + 1`), b2s_scan_i64 turns them into indptr, the caller
+ * reads nnz = indptr[nrows], allocates indices/data and runs the fill pass.
+ * ---------------------------------------------------------------------- */
+int64_t b2s_scan_workspace_bytes(int64_t n);
+/* indptr[0] = 0, indptr[i+1] = counts[0] + .. + counts[i], counts = indptr[1..n] on entry */
+int b2s_scan_i64(int64_t n, int64_t* indptr, void* workspace, int64_t workspace_bytes,
+                 b2s_stream_t stream);
+/* DenseToCSRNNZ / DenseToCSR: src/sparse/array/conv/dense_to_csr.cu:25-43,128-149 (`!= 0` test,
+ * CPU loops dense_to_csr.cc:32-40,55-64).  dense is row-major with leading dimension ld. */
+int b2s_dense_to_csr_count(b2s_dtype vt, int64_t nrows, int64_t ncols, int64_t ld,
+                           const void* dense, int64_t* row_nnz, b2s_stream_t stream);
+int b2s_dense_to_csr_fill(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t ld,
+                          const void* dense, const int64_t* indptr, void* indices, void* data,
+                          b2s_stream_t stream);
+/* dia_array.tocsr: legate_sparse/dia.py:159-190 (cupynumeric ops upstream).  data[d*ld + j] is
+ * A[j - offsets[d], j] for j < width; `order` lists the diagonals by ascending offset (columns
+ * come out sorted); explicit zeros are dropped (dia.py:171). */
+int b2s_dia_to_csr_count(b2s_dtype vt, int64_t nrows, int64_t ncols, int ndiag, int64_t width,
+                         int64_t ld, const void* data, const int64_t* offsets, const int* order,
+                         int64_t* row_nnz, b2s_stream_t stream);
+int b2s_dia_to_csr_fill(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int ndiag,
+                        int64_t width, int64_t ld, const void* data, const int64_t* offsets,
+                        const int* order, const int64_t* indptr, void* indices, void* out_data,
+                        b2s_stream_t stream);
+/* legate_sparse.random (no upstream counterpart: the reference's tests densify cupynumeric
+ * random arrays, tests/integration/utils/sample.py:21-45).  Counter-based: rows [r0, r1) of an
+ * m x n matrix with exactly nnz_total entries, k_i = nnz_total/m (+1 for nnz_total%m rows) per
+ * row, the j-th entry of a row in the j-th of k_i equal strata of [0, n) (sorted, distinct),
+ * values uniform in [lo, hi).  Entry (i, j) depends only on (seed, i, j). */
+int b2s_random_csr_rowptr(int64_t m, int64_t nnz_total, uint64_t seed, int64_t r0, int64_t r1,
+                          int64_t* indptr_local, b2s_stream_t stream);
+int64_t b2s_random_csr_block_nnz(int64_t m, int64_t nnz_total, uint64_t seed, int64_t r0, int64_t r1);
+int b2s_random_csr_fill(b2s_dtype vt, b2s_itype it, int64_t m, int64_t n, int64_t nnz_total,
+                        uint64_t seed, int64_t r0, int64_t r1, double lo, double hi, void* indices,
+                        void* data, b2s_stream_t stream);
 
 #ifdef __cplusplus
 }

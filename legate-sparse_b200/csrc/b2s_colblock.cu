@@ -11,8 +11,8 @@
 // gathers from one <= ~40 MB slice of x.  Extra traffic: one more pass over indptr and y per block.
 //
 // Replaces nothing in the reference by itself: it is a plan-time layout of the operand of
-// legate_sparse's CSR SpMV task (src/legate_sparse/array/csr/spmv.cu:27-75), like cuSPARSE's
-// preprocess step there.
+// legate_sparse's CSR SpMV task body (src/sparse/array/csr/spmv.cu:30-163): the reference hands the
+// whole row block to one cusparseSpMV call (spmv.cu:117-152) and has no operand preparation of its own.
 #include "b2s_common.cuh"
 
 #include <cstdlib>
@@ -285,14 +285,14 @@ extern "C" int b2s_csr_colblock_create(b2s_dtype vt, b2s_itype it, int64_t nrows
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { delete C; set_error("colblock scatter failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
   }
-  // one SpMV plan per block; with an L2-resident x slice the 2048-nnz tile measured faster unless
-  // rows are very short (more than ~128 rows per tile)
+  // one SpMV plan per block, 1024-nnz tiles: the two ping-pong consumer groups of the pipe kernel
+  // measured fastest with them (2.23 ms vs 2.47 ms with 2048-nnz tiles on C2, profiles/r2_pipe_sweep.txt)
   for (int b = 0; b < nb && rc == B2S_OK; ++b) {
     if (C->blk_nnz[b] == 0) continue;
     const int64_t wsb = b2s_spmv_plan_workspace_bytes(nrows, C->blk_nnz[b]);
     uintptr_t pb = ((uintptr_t)plan_base + 255) & ~(uintptr_t)255;
     if (reinterpret_cast<unsigned char*>(pb) + wsb > ws_end) { set_error("colblock workspace carve overflow"); rc = B2S_ERR_WORKSPACE; break; }
-    const int64_t tile = (C->blk_nnz[b] / nrows >= 16) ? 2048 : 1024;
+    const int64_t tile = 1024;
     rc = plan_create_impl(it, nrows, ncols, C->blk_nnz[b], C->indptr[b], C->cols[b], reinterpret_cast<void*>(pb), wsb,
                           stream, tile, &C->plan[b]);
     plan_base = reinterpret_cast<unsigned char*>(pb) + wsb;

@@ -34,10 +34,7 @@ struct PlanHeader {  // host-side plan object
   int64_t* tile_win;   // [2*ntiles]  (aligned base col, count) ; count==0 → no window
   void*    head;       // [ntiles] * 16 bytes
   void*    dotp;       // [ntiles] * 16 bytes (per-tile partials of the fused dot)
-  void*    sub_head;   // [ntiles*8] * 16 bytes  (merge kernel: per-warp-sub-tile head pieces)
-  int64_t* sub_head_row;  // [ntiles*8]          (row*2+first_continuation, or -1)
   int64_t  empty_rows; // number of rows without non-zeros
-  int64_t* sub_row;    // [ntiles*8 + 2] first row of every 128-nnz sub-tile (1024-nnz plans)
   int64_t* counters;   // [4]
 };
 
@@ -330,46 +327,59 @@ spmv_rowvec_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const I* _
 
 }  // namespace b2s
 #include "b2s_spmv_pipe.cuh"
-#include "b2s_spmv_merge.cuh"
-#include "b2s_spmv_wpipe.cuh"
 namespace b2s {
 
 // ------------------------------------------------------------------ host launchers
 static int num_sms() {
-  static int n = [] {
-    int dev = 0, v = kNumSMs;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : kNumSMs;
-  }();
-  return n;
+  int dev = 0, v = kNumSMs;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  return v > 0 ? v : kNumSMs;
 }
 
-template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool BCAST>
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Products-consumer configuration (tools/spmv_sweep varies it through the environment):
+//   B2S_SPMV_GROUPS   1 | 2      consumer groups per CTA (default 2: ping-pong)
+static int pipe_groups_default() { int g = env_int("B2S_SPMV_GROUPS", 2); return g == 1 ? 1 : 2; }
+
+template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG>
 static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
                             const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
-  using L = PipeLayout<V, I, IPT>;
+  using L = PipeLayout<V, I, TILE>;
   const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
-  auto kern = spmv_pipe_kernel<V, I, IPT, STAGES, WINDOW, DOT, BCAST>;
-  static int blocks_per_sm = -1;  // per instantiation
-  if (blocks_per_sm < 0) {
+  auto kern = spmv_pipe_kernel<V, I, TILE, STAGES, WINDOW, DOT, BCAST, NG>;
+  // function attributes are per device: cache the resident-CTA count per (instantiation, device)
+  static std::atomic<int> blocks_per_sm[kMaxDevices];
+  const int dev = current_device();
+  int nb = blocks_per_sm[dev].load(std::memory_order_acquire);
+  if (nb <= 0) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // Every x gather in flight holds an L1 line, so the gather-bound products kernel wants L1, not
-    // shared memory: on 2048-nnz tiles (57.6 KB per CTA) two CTAs with the 132 KB shared-memory
-    // configuration (L1 = 124 KB) beat the three CTAs the occupancy API offers (196 KB, L1 = 60 KB):
-    // 2.30 vs 2.375 ms on the column-blocked C2 matrix; a 228 KB carve-out costs 65 %
-    // (tools/gpu_occ.sh).  B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
-    int carve = (!WINDOW && IPT == 8) ? 55 : -1, cap = (!WINDOW && IPT == 8) ? 2 : 0;
-    if (const char* e = getenv("B2S_SPMV_CARVEOUT")) carve = atoi(e);
-    if (const char* e = getenv("B2S_SPMV_CTAS")) cap = atoi(e);
+    // shared memory: two CTAs with the 132 KB shared-memory configuration (L1 = 124 KB) beat the
+    // three CTAs the occupancy API offers (196 KB, L1 = 60 KB): 2.30 vs 2.375 ms on the
+    // column-blocked C2 matrix; a 228 KB carve-out costs 65 % (tools/gpu_occ.sh).
+    // B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
+    int carve = !WINDOW ? 55 : -1, cap = !WINDOW ? 2 : 0;
+    carve = env_int("B2S_SPMV_CARVEOUT", carve);
+    cap = env_int("B2S_SPMV_CTAS", cap);
     if (carve >= 0) B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int nb = 0;
     B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
     if (nb < 1) { set_error("spmv_pipe_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
     if (cap >= 1 && cap < nb) nb = cap;
-    blocks_per_sm = nb;
+    blocks_per_sm[dev].store(nb, std::memory_order_release);
   }
-  int64_t grid = (int64_t)blocks_per_sm * num_sms();
+  int64_t grid = (int64_t)nb * num_sms();
   if (grid > P->ntiles) grid = P->ntiles;
   *npartials = grid;
   kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals,
@@ -380,99 +390,24 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   return B2S_OK;
 }
 
-template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT>
-static int launch_merge_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
-                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                             cudaStream_t st) {
-  using L = PipeLayout<V, I, IPT>;
-  const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
-  auto kern = spmv_merge_kernel<V, I, IPT, STAGES, WINDOW, DOT>;
-  static int blocks_per_sm = -1;  // per instantiation
-  if (blocks_per_sm < 0) {
-    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
-    if (nb < 1) { set_error("spmv_merge_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
-    blocks_per_sm = nb;
-  }
-  int64_t grid = (int64_t)blocks_per_sm * num_sms();
-  if (grid > P->ntiles) grid = P->ntiles;
-  *npartials = grid;
-  kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles,
-                                                   P->empty_rows > 0 ? 1 : 0, indptr, cols, vals, x, y,
-                                                   P->tile_row, P->tile_win, reinterpret_cast<V*>(P->sub_head),
-                                                   P->sub_head_row, dot_partials, w);
-  B2S_CHECK_LAUNCH();
-  const int64_t nsub = P->ntiles * (kPipeConsumers / 32);
-  spmv_subfixup_kernel<V><<<(unsigned)ceil_div(nsub, 256), 256, 0, st>>>(
-      nsub, P->sub_head_row, reinterpret_cast<const V*>(P->sub_head), y);
-  B2S_CHECK_LAUNCH();
-  return B2S_OK;
-}
-
-template <typename V, typename I, int STAGES, bool DOT>
-static int launch_wpipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
-                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                             cudaStream_t st) {
-  using L = PipeLayout<V, I, 4>;
-  const size_t stage = (L::xwin_off + 16 * 8 + 127) / 128 * 128;
-  const size_t smem = stage * STAGES + 16 * STAGES;
-  auto kern = spmv_wpipe_kernel<V, I, STAGES, DOT>;
-  static int blocks_per_sm = -1;  // per instantiation
-  if (blocks_per_sm < 0) {
-    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
-    if (nb < 1) { set_error("spmv_wpipe_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
-    blocks_per_sm = nb;
-  }
-  int64_t grid = (int64_t)blocks_per_sm * num_sms();
-  if (grid > P->ntiles) grid = P->ntiles;
-  *npartials = grid;
-  kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles,
-                                                   P->empty_rows > 0 ? 1 : 0, indptr, cols, vals, x, y,
-                                                   P->sub_row, reinterpret_cast<V*>(P->sub_head),
-                                                   P->sub_head_row, dot_partials, w);
-  B2S_CHECK_LAUNCH();
-  const int64_t nsub = P->ntiles * (kPipeConsumers / 32);
-  spmv_subfixup_kernel<V><<<(unsigned)ceil_div(nsub, 256), 256, 0, st>>>(
-      nsub, P->sub_head_row, reinterpret_cast<const V*>(P->sub_head), y);
-  B2S_CHECK_LAUNCH();
-  return B2S_OK;
-}
-
-static int pipe_stages_default(int ipt) {
-  const char* e = getenv("B2S_SPMV_STAGES");
-  int s = e ? atoi(e) : (ipt == 4 ? 3 : 2);
-  return (s < 2 || s > 4) ? 2 : s;
-}
-
-template <typename V, typename I, int IPT, bool DOT>
-static int launch_pipe_ipt(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
-                           const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                           const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
-  bool window = (P->window_tiles * 2 >= P->ntiles) && ((uintptr_t)x % 16 == 0) &&
-                getenv("B2S_SPMV_NO_WINDOW") == nullptr;
-  // window matrices (banded / stencil): row-walk consumer; others: products consumer (chosen by
-  // WINDOW inside the kernel).  Only STAGES = 2 is instantiated (deeper rings cost CTAs/SM and
-  // measured slower).  Peer stores are compiled in only for the broadcast launches.
-  const bool bcast = peers.n != 0;
-#define B2S_PIPE(W, B) launch_pipe_inst<V, I, IPT, 2, W, DOT, B>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, accumulate, st)
-  if (window) return bcast ? B2S_PIPE(true, true) : B2S_PIPE(true, false);
-  return bcast ? B2S_PIPE(false, true) : B2S_PIPE(false, false);
-#undef B2S_PIPE
-}
-
-template <typename V, typename I, int IPT, bool DOT>
-static int launch_merge_ipt(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
+template <typename V, typename I, int TILE, bool DOT>
+static int launch_pipe_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
-                            cudaStream_t st) {
+                            const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
   bool window = (P->window_tiles * 2 >= P->ntiles) && ((uintptr_t)x % 16 == 0) &&
                 getenv("B2S_SPMV_NO_WINDOW") == nullptr;
-#define B2S_MRG(W) launch_merge_inst<V, I, IPT, 2, W, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, st)
-  if (window) return B2S_MRG(true);
-  return B2S_MRG(false);
-#undef B2S_MRG
+  // window matrices (banded / stencil): row-walk consumer, 2-stage ring; others: products consumer
+  // with two ping-pong consumer groups on a 4-stage ring of 1024-nnz tiles (or one group / 2 stages).
+  // Peer stores are compiled in only for the broadcast launches.
+  const bool bcast = peers.n != 0;
+#define B2S_PIPE(S, W, B, G) launch_pipe_inst<V, I, TILE, S, W, DOT, B, G>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, accumulate, st)
+  if (window) return bcast ? B2S_PIPE(2, true, true, 1) : B2S_PIPE(2, true, false, 1);
+  if (pipe_groups_default() == 2) {
+    if constexpr (TILE == 1024) return bcast ? B2S_PIPE(4, false, true, 2) : B2S_PIPE(4, false, false, 2);
+    else                        return bcast ? B2S_PIPE(2, false, true, 2) : B2S_PIPE(2, false, false, 2);
+  }
+  return bcast ? B2S_PIPE(2, false, true, 1) : B2S_PIPE(2, false, false, 1);
+#undef B2S_PIPE
 }
 
 // pipe kernel needs 16-byte aligned streams (TMA bulk copies) and a 1024/2048 tile
@@ -487,10 +422,11 @@ static int launch_tile_inst(const PlanHeader* P, const int64_t* indptr, const I*
   constexpr int T = kTileThreads * IPT;
   size_t smem = sizeof(V) * T + (WINDOW ? sizeof(V) * kWinCap + 16 : 0);
   auto kern = spmv_tile_kernel<V, I, IPT, VEC, WINDOW, DOT>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static std::atomic<int> attr_set[kMaxDevices];  // per (instantiation, device): attributes are per device
+  const int dev = current_device();
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[dev].store(1, std::memory_order_release);
   }
   kern<<<(unsigned)P->ntiles, kTileThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, indptr, cols, vals,
                                                         x, y, P->tile_row, P->tile_win,
@@ -519,29 +455,9 @@ static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, c
                     const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
   int rc;
   int64_t npartials = P->ntiles;
-  if (mode == 3) {
-    const char* e = getenv("B2S_SPMV_STAGES");
-    if (e && atoi(e) == 3) rc = launch_wpipe_inst<V, I, 3, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
-    else                   rc = launch_wpipe_inst<V, I, 2, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
-    if (rc) return rc;
-    if (DOT) {
-      reduce_partials_kernel<V><<<1, 1024, 0, st>>>(npartials, dot_partials, dot_out);
-      B2S_CHECK_LAUNCH();
-    }
-    return B2S_OK;
-  }
-  if (mode == 2) {
-    if (P->tile_nnz == 1024) rc = launch_merge_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
-    else                     rc = launch_merge_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, st);
-    if (rc) return rc;
-    if (DOT) {
-      reduce_partials_kernel<V><<<1, 1024, 0, st>>>(npartials, dot_partials, dot_out);
-      B2S_CHECK_LAUNCH();
-    }
-    return B2S_OK;   // the merge path has its own fix-up (sub-tile granularity)
-  } else if (mode == 1) {
-    if (P->tile_nnz == 1024) rc = launch_pipe_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, accumulate, st);
-    else                     rc = launch_pipe_ipt<V, I, 8, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, accumulate, st);
+  if (mode == 1) {
+    if (P->tile_nnz == 1024) rc = launch_pipe_tile<V, I, 1024, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, accumulate, st);
+    else                     rc = launch_pipe_tile<V, I, 2048, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, &npartials, peers, accumulate, st);
   } else
   switch (P->tile_nnz) {
     case 1024: rc = launch_tile_ipt<V, I, 4, DOT>(P, indptr, cols, vals, x, y, dot_partials, w, st); break;
@@ -614,7 +530,7 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
     return B2S_OK;
   }
   bool use_tile = (P != nullptr) && (variant != B2S_SPMV_ROWVEC);
-  if ((variant == B2S_SPMV_TILE || variant == B2S_SPMV_PIPE || variant == B2S_SPMV_MERGE || variant == B2S_SPMV_WPIPE) && P == nullptr) {
+  if ((variant == B2S_SPMV_TILE || variant == B2S_SPMV_PIPE) && P == nullptr) {
     set_error("B2S_SPMV_TILE / B2S_SPMV_PIPE require a plan");
     return B2S_ERR_ARG;
   }
@@ -628,19 +544,12 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
       return B2S_ERR_ARG;
     }
     const bool tma_ok = pipe_ok(P, indptr, cols, vals);
-    if ((variant == B2S_SPMV_PIPE || variant == B2S_SPMV_MERGE) && !tma_ok) {
-      set_error("B2S_SPMV_PIPE/MERGE need 16-byte aligned indptr/indices/data and a 1024/2048-nnz plan");
+    if (variant == B2S_SPMV_PIPE && !tma_ok) {
+      set_error("B2S_SPMV_PIPE needs 16-byte aligned indptr/indices/data and a 1024/2048-nnz plan");
       return B2S_ERR_ARG;
     }
     int mode = 0;
-    if (tma_ok && variant != B2S_SPMV_TILE) mode = (variant == B2S_SPMV_MERGE) ? 2 : 1;
-    if (variant == B2S_SPMV_WPIPE) {
-      if (!tma_ok || P->tile_nnz != 1024 || peers.n != 0) {
-        set_error("B2S_SPMV_WPIPE needs aligned arrays, a 1024-nnz plan and no peer broadcast");
-        return B2S_ERR_ARG;
-      }
-      mode = 3;
-    }
+    if (tma_ok && variant != B2S_SPMV_TILE) mode = 1;
     if (peers.n != 0 && mode != 1) {
       set_error("peer broadcast needs the pipe kernel (16-byte aligned arrays, 1024/2048-nnz plan)");
       return B2S_ERR_UNSUPPORTED;
@@ -669,7 +578,7 @@ extern "C" int64_t b2s_spmv_plan_workspace_bytes(int64_t nrows, int64_t nnz) {
   if (nnz < 0) return -1;
   int64_t ntiles = ceil_div(nnz > 0 ? nnz : 1, 1024);  // smallest tile → upper bound
   // tile_row (ntiles+1) + tile_win (2*ntiles) int64, head 16 B/tile, counters, padding
-  return (ntiles + 1) * 8 + ntiles * 16 + ntiles * 16 + ntiles * 16 + ntiles * 8 * 24 + (ntiles * 8 + 4) * 8 + 64 + 1024;
+  return (ntiles + 1) * 8 + ntiles * 16 + ntiles * 16 + ntiles * 16 + 64 + 1024;
 }
 
 namespace b2s {
@@ -710,10 +619,6 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
     P->tile_win = reinterpret_cast<int64_t*>(base);               base += nt * 16;
     P->head = reinterpret_cast<void*>(base);                      base += nt * 16;
     P->dotp = reinterpret_cast<void*>(base);                      base += nt * 16;
-    P->sub_head = reinterpret_cast<void*>(base);                  base += nt * 8 * 16;
-    P->sub_head_row = reinterpret_cast<int64_t*>(base);           base += nt * 8 * 8;
-    base = (base + 63) & ~(uintptr_t)63;
-    P->sub_row = reinterpret_cast<int64_t*>(base);
     P->empty_rows = 0;
     if (nt == 0) break;
     cudaError_t e = cudaMemsetAsync(P->counters, 0, 64, st);
@@ -743,12 +648,6 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
     P->window_tiles = h[0];
     P->head_tiles = h[1];
     P->empty_rows = h[2];
-    if (P->tile_nnz == 1024) {
-      // first row of every 128-nnz sub-tile (+2 sentinel entries) for the warp-autonomous kernel
-      const int64_t nsub = nt * 8;
-      plan_tile_rows_kernel<<<(unsigned)ceil_div(nsub + 2, 256), 256, 0, st>>>(nrows, nsub + 1, 128, indptr, P->sub_row);
-      g_launch_count.fetch_add(1);
-    }
     if (forced || P->window_tiles * 2 >= P->ntiles) break;   // keep this tiling
   }
   *out_plan = P;
@@ -786,7 +685,7 @@ int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t
   B2S_REQUIRE(nrows == 0 || y != nullptr, "y is null");
   B2S_REQUIRE(nrows == 0 || indptr != nullptr, "indptr is null");
   B2S_REQUIRE(nnz == 0 || (indices && data && x), "null matrix/vector arrays");
-  B2S_REQUIRE(variant >= B2S_SPMV_AUTO && variant <= B2S_SPMV_WPIPE, "bad variant");
+  B2S_REQUIRE(variant >= B2S_SPMV_AUTO && variant <= B2S_SPMV_PIPE, "bad variant");
   cudaStream_t st = (cudaStream_t)stream;
   B2S_DISPATCH_VT(vt, V, {
     PeerOut<V> peers{};

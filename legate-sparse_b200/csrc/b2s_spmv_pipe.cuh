@@ -11,11 +11,17 @@
 //     says the tile's [min col, max col] image is small (banded / stencil matrices; the
 //     reference's image(crd→x, MIN_MAX), csr.py:591) — the x window itself.  The streams never
 //     touch the LSU/L1TEX path or the register file, so that path is left to the x gathers;
-//   * 8 CONSUMER warps: wait on the stage's "full" mbarrier; a group of 1..32 lanes owns one row
-//     of the tile, walks its (col,val) pairs in shared memory, gathers x (shared-memory window,
-//     else L2 with an evict_last policy), accumulates in registers, shuffle-reduces in a fixed
-//     order and writes y; then each thread arrives on the stage's "empty" mbarrier.  There is
-//     no CTA-wide barrier per tile and no floating-point atomics.
+//   * 8 CONSUMER warps, two flavours (chosen per matrix, see spmv_pipe_kernel):
+//       row-walk  (window matrices): a group of 1..32 lanes owns one row of the staged tile, walks
+//                 its (col,val) pairs in shared memory, reads x from the staged window, accumulates
+//                 in registers, shuffle-reduces in a fixed order and writes y.  No CTA-wide barrier.
+//       products  (x gathered from L2): the consumers form NG independent groups of 256/NG threads
+//                 that take the CTA's tiles in turn (group g owns ring stages s = g mod NG), so that
+//                 one group's gather phase overlaps the other's reduction phase.  Every thread issues
+//                 all of its gathers at once for 16-byte chunks of the staged (col,val) slices
+//                 (conflict-free LDS/STS), parks the products in place, and after the group's named
+//                 barrier the rows are reduced out of shared memory by 1..32 lanes per row.
+//     No floating-point atomics anywhere: results are bit-reproducible.
 #pragma once
 
 namespace b2s {
@@ -34,9 +40,9 @@ struct PipeMeta {  // written by the producer before it arms the full barrier
   int32_t pad;
 };
 
-template <typename V, typename I, int IPT>
+template <typename V, typename I, int TILE>
 struct PipeLayout {
-  static constexpr int T = kPipeConsumers * IPT;
+  static constexpr int T = TILE;
   static constexpr int RCAP = T / 4 + 4;            // indptr entries per stage
   static constexpr size_t vals_off = 0;
   static constexpr size_t cols_off = vals_off + sizeof(V) * T;
@@ -51,15 +57,32 @@ struct PipeLayout {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void consumer_bar_sync() {
+__device__ __forceinline__ void consumer_bar_sync() {   // all consumer warps (not the producer)
   asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumers) : "memory");
 }
+template <int GT>
+__device__ __forceinline__ void group_bar_sync(int grp) {   // one consumer group of GT threads
+  asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(GT) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  // generic-proxy accesses to a stage (product stores, reads) before the async proxy (TMA) refills it
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// lanes per row of a tile with nr candidate rows handled by gt threads
+__device__ __forceinline__ int lanes_for(int64_t nr, int gt) {
+  int lanes = 1;
+  while (lanes < 32 && (int64_t)(lanes * 2) * nr <= gt) lanes <<= 1;
+  return lanes;
+}
+template <typename V, int C> struct alignas(16) VChunk { V v[C]; };
+template <typename I, int C> struct alignas((sizeof(I) * C) < 16 ? (sizeof(I) * C) : 16) IChunk { I c[C]; };
 
 // WINDOW also selects the consumer: window matrices (banded / stencil) use the row-walk consumer,
 // all others the products consumer (each measured fastest there; the cross combinations were never
 // faster and are not instantiated).  BCAST compiles the peer stores in; the plain instances carry
 // no trace of them (the peer ranges cost the banded kernel 13% when they were a runtime branch).
-template <typename V, typename I, int IPT, int STAGES, bool WINDOW, bool DOT, bool BCAST>
+// NG = consumer groups of the products consumer (1 or 2; STAGES must be a multiple of NG).
+template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG>
 __global__ void __launch_bounds__(kPipeThreads)
 spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const int64_t* __restrict__ indptr, const I* __restrict__ cols,
@@ -67,9 +90,11 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const int64_t* __restrict__ tile_row, const int64_t* __restrict__ tile_win,
                  V* __restrict__ head, V* __restrict__ dot_partials, const V* __restrict__ w,
                  const PeerOut<V> peers, const int accumulate) {
-  using L = PipeLayout<V, I, IPT>;
+  using L = PipeLayout<V, I, TILE>;
   constexpr int T = L::T;
   constexpr bool ROWWALK = WINDOW;
+  constexpr int GT = kPipeConsumers / NG;          // threads per consumer group
+  static_assert(STAGES % NG == 0 && (NG == 1 || !WINDOW), "bad consumer grouping");
   constexpr size_t STAGE = L::stage_bytes(WINDOW);
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + STAGE * STAGES);
@@ -78,7 +103,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kPipeConsumers); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ROWWALK ? kPipeConsumers : GT); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -94,6 +119,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         const int s = (int)(i % STAGES);
         const uint32_t ph = (uint32_t)((i / STAGES) & 1);
         mbar_wait(&empty_bar[s], ph ^ 1u);
+        fence_proxy_async_smem();
         unsigned char* st = smem + STAGE * s;
         PipeMeta* meta = reinterpret_cast<PipeMeta*>(st + L::meta_off);
         const int64_t S = t * (int64_t)T;
@@ -142,13 +168,36 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
 
   // ================================== CONSUMERS ==================================
   if constexpr (!ROWWALK) {
-    // "products" consumer (matrices whose x gathers go to L2): every thread issues IPT independent
-    // gathers for IPT staged (col,val) pairs (nnz-balanced, maximal memory-level parallelism),
-    // parks the products in place, and after one named barrier the tile's rows are reduced by
-    // 1..32 lanes per row out of shared memory.
-    int64_t i = 0;
+    // "products" consumer (matrices whose x gathers go to L2).  Group `grp` owns the CTA's tiles
+    // i = grp, grp+NG, ... (ring stage i % STAGES).  Per tile: every thread issues ALL its gathers
+    // at once (nnz-balanced, maximal memory-level parallelism) for NCH chunks of 16 bytes of values,
+    // parks the products in place, and after the group's named barrier the tile's rows are reduced
+    // by 1..32 lanes per row out of shared memory.
+    constexpr int C   = (16 / (int)sizeof(V)) > 0 ? (16 / (int)sizeof(V)) : 1;   // values per 16-byte chunk
+    constexpr int NCH = T / (GT * C);                                           // chunks per thread
+    static_assert(NCH * GT * C == T, "tile size must be a multiple of the group's chunk footprint");
+    using VC = VChunk<V, C>;
+    using IC = IChunk<I, C>;
+    const int grp = tid / GT, gtid = tid % GT;
     V dot_acc = zero_of<V>();
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+    // y += A_b x (later column blocks): the old y of this thread's first row is fetched ONE TILE
+    // AHEAD (the rows of the next tile are known from the plan), so that its DRAM latency never
+    // sits in front of a store
+    auto prefetch_y = [&](int64_t tn) -> V {
+      if (!accumulate || tn >= ntiles) return zero_of<V>();
+      const int64_t rb = tile_row[tn], rl = tile_row[tn + 1];
+      const int64_t nrn = rl - rb + 1;
+      const int ln = lanes_for(nrn, GT);
+      const int64_t slot = gtid / ln;
+      if ((gtid & (ln - 1)) == 0 && slot < nrn && rb + slot < nrows) return y[rb + slot];
+      return zero_of<V>();
+    };
+    V ynext = prefetch_y((int64_t)blockIdx.x + (int64_t)grp * gridDim.x);
+    for (int64_t i = grp; ; i += NG) {
+      const int64_t t = (int64_t)blockIdx.x + i * (int64_t)gridDim.x;
+      if (t >= ntiles) break;
+      const V ypre = ynext;
+      ynext = prefetch_y(t + (int64_t)NG * gridDim.x);
       const int s = (int)(i % STAGES);
       const uint32_t ph = (uint32_t)((i / STAGES) & 1);
       mbar_wait(&full_bar[s], ph);
@@ -156,51 +205,55 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
       V* svals = reinterpret_cast<V*>(st + L::vals_off);
       const I* scols = reinterpret_cast<const I*>(st + L::cols_off);
       const int64_t* srptr = reinterpret_cast<const int64_t*>(st + L::rptr_off);
-      const V* sxwin = reinterpret_cast<const V*>(st + L::xwin_off);
       const PipeMeta meta = *reinterpret_cast<const PipeMeta*>(st + L::meta_off);
       const int64_t S = t * (int64_t)T;
       const int64_t E = min(S + (int64_t)T, nnz);
-      const bool use_win = WINDOW && meta.win_staged;
       const int64_t r_begin = meta.r_begin, r_last = meta.r_last;
       const int64_t nr = r_last - r_begin + 1;
-      int lanes = 1;
-      while (lanes < 32 && (int64_t)(lanes * 2) * nr <= kPipeConsumers) lanes <<= 1;
-      const int groups = kPipeConsumers / lanes;
-      const int gl = tid & (lanes - 1);
-      // y += A_b x: fetch the old y of this thread's first row now, so that its latency hides
-      // behind the gathers instead of sitting in front of the store
-      V ypre = zero_of<V>();
-      if (accumulate && gl == 0 && tid / lanes < nr && r_begin + tid / lanes < nrows) ypre = y[r_begin + tid / lanes];
+      const int lanes = lanes_for(nr, GT);
+      const int groups = GT / lanes;
+      const int gl = gtid & (lanes - 1);
       if (meta.full_tile) {
+        // Gathers are issued in batches of BCH chunks = 4 gathers per thread.  Measured on the
+        // column-blocked C2 matrix (profiles/r2_pipe_sweep.txt): all 8 of a thread at once 2.40 ms,
+        // 4 at a time 2.29 ms, 2 at a time 2.41 ms; with L1::no_allocate on the gathers (their L1
+        // hit rate is 0.5 %, so a line per outstanding request buys nothing) 2.23 ms.
+        constexpr int BCH = (4 / C) > 0 ? ((4 / C) < NCH ? (4 / C) : NCH) : 1;
+        static_assert(NCH % BCH == 0, "chunks per thread must be a multiple of the gather batch");
 #pragma unroll
-        for (int g = 0; g < IPT / 4; ++g) {
-          const int q = (g * kPipeConsumers + tid) * 4;
-          I c[4];
-          V v[4];
-          memcpy(c, scols + q, sizeof(I) * 4);   // LDS.128
-          memcpy(v, svals + q, sizeof(V) * 4);
-          V xv[4];
+        for (int k = 0; k < NCH; k += BCH) {
+          IC pc[BCH];
+          VC pv[BCH];
+          V xv[BCH][C];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (use_win) xv[k] = sxwin[(int64_t)c[k] - meta.wbase];
-            else         xv[k] = ld_gather<V>(x + (int64_t)c[k], pol_keep);
+          for (int u = 0; u < BCH; ++u) {
+            const int e = ((k + u) * GT + gtid) * C;
+            pc[u] = *reinterpret_cast<const IC*>(scols + e);   // LDS.64 / LDS.128, conflict-free
+            pv[u] = *reinterpret_cast<const VC*>(svals + e);   // LDS.128, conflict-free
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = vmul(v[k], xv[k]);
-          memcpy(svals + q, v, sizeof(V) * 4);   // STS.128
+          for (int u = 0; u < BCH; ++u)
+#pragma unroll
+            for (int j = 0; j < C; ++j) xv[u][j] = ld_gather_na<V>(x + (int64_t)pc[u].c[j], pol_keep);
+#pragma unroll
+          for (int u = 0; u < BCH; ++u) {
+#pragma unroll
+            for (int j = 0; j < C; ++j) pv[u].v[j] = vmul(pv[u].v[j], xv[u][j]);
+            *reinterpret_cast<VC*>(svals + ((k + u) * GT + gtid) * C) = pv[u];   // STS.128, conflict-free
+          }
+          asm volatile("" ::: "memory");   // keep the batches apart (the compiler would merge them)
         }
       } else {
-        for (int64_t p = S + tid; p < E; p += kPipeConsumers) {
+        for (int64_t p = S + gtid; p < E; p += GT) {
           int64_t c = (int64_t)ld_stream<I>(cols + p, pol_stream);
           V a = ld_stream<V>(vals + p, pol_stream);
-          V xx = use_win ? sxwin[c - meta.wbase] : ld_gather<V>(x + c, pol_keep);
-          svals[p - S] = vmul(a, xx);
+          svals[p - S] = vmul(a, ld_gather_na<V>(x + c, pol_keep));
         }
       }
-      consumer_bar_sync();
+      if constexpr (NG == 1) consumer_bar_sync(); else group_bar_sync<GT>(grp);
       for (int64_t base = 0; base < nr; base += groups) {
-        const int64_t r = r_begin + base + tid / lanes;
-        const bool valid = (base + tid / lanes < nr) && (r < nrows);
+        const int64_t r = r_begin + base + gtid / lanes;
+        const bool valid = (base + gtid / lanes < nr) && (r < nrows);
         int64_t lo_g = 0, hi_g = 0;
         if (valid) {
           if (meta.rows_staged) { lo_g = srptr[r - meta.ra]; hi_g = srptr[r - meta.ra + 1]; }
@@ -227,6 +280,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
         }
       }
+      fence_proxy_async_smem();
       mbar_arrive(&empty_bar[s]);
     }
     if (DOT) {

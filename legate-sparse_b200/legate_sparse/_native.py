@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb200sparse.so"))
@@ -21,7 +21,7 @@ _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb200sparse.so"
 # enums (include/b200sparse.h)
 B2S_F32, B2S_F64, B2S_C64, B2S_C128 = 0, 1, 2, 3
 B2S_I32, B2S_I64 = 0, 1
-B2S_SPMV_AUTO, B2S_SPMV_ROWVEC, B2S_SPMV_TILE, B2S_SPMV_PIPE, B2S_SPMV_MERGE = 0, 1, 2, 3, 4
+B2S_SPMV_AUTO, B2S_SPMV_ROWVEC, B2S_SPMV_TILE, B2S_SPMV_PIPE = 0, 1, 2, 3
 
 _lib = None
 _load_error = None
@@ -74,6 +74,15 @@ SIGNATURES = {
     "b2s_cast_i64_to_i32": (c_int, [_I64, _P, _P, _P]),
     "b2s_cast_i32_to_i64": (c_int, [_I64, _P, _P, _P]),
     "b2s_csr_to_dense": (c_int, [c_int, c_int, _I64, _I64, _P, _P, _P, _P, _P]),
+    "b2s_scan_workspace_bytes": (_I64, [_I64]),
+    "b2s_scan_i64": (c_int, [_I64, _P, _P, _I64, _P]),
+    "b2s_dense_to_csr_count": (c_int, [c_int, _I64, _I64, _I64, _P, _P, _P]),
+    "b2s_dense_to_csr_fill": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
+    "b2s_dia_to_csr_count": (c_int, [c_int, _I64, _I64, c_int, _I64, _I64, _P, _P, _P, _P, _P]),
+    "b2s_dia_to_csr_fill": (c_int, [c_int, c_int, _I64, _I64, c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "b2s_random_csr_rowptr": (c_int, [_I64, _I64, c_uint64, _I64, _I64, _P, _P]),
+    "b2s_random_csr_block_nnz": (_I64, [_I64, _I64, c_uint64, _I64, _I64]),
+    "b2s_random_csr_fill": (c_int, [c_int, c_int, _I64, _I64, _I64, c_uint64, _I64, _I64, c_double, c_double, _P, _P, _P]),
 }
 
 

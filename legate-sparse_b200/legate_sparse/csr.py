@@ -97,13 +97,20 @@ class csr_array(CompressedBase):
         self._blk = None
         self._bounds = None
         self._B_full = None  # replicated device copy used when this matrix is the B of A@B
+        self._nnz_per_rank = None
 
         if dtype is not None:
             dtype = numpy.dtype(dtype)
 
-        # dense torch tensor → numpy (construction is host-side)
+        # dense CUDA tensor → CSR on the device (two-pass count / fill with a `!= 0` test:
+        # reference dense_to_csr.cu:25-43,128-149); a dense CPU tensor goes the numpy way below
         if isinstance(arg, torch.Tensor) and arg.dim() == 2:
-            arg = arg.detach().cpu().numpy()
+            if arg.is_cuda:
+                shape = tuple(arg.shape)
+                arg = _dense_to_csr_device(arg)
+                copy = False
+            else:
+                arg = arg.detach().numpy()
 
         if isinstance(arg, (scipy.sparse.csr_array, scipy.sparse.csr_matrix)):
             shape = arg.shape
@@ -134,6 +141,10 @@ class csr_array(CompressedBase):
                 self._g_data = arg._g_data.clone()
                 self._g_indices = arg._g_indices.clone()
                 self._g_indptr = arg._g_indptr.clone()
+            if arg._h_data is None and arg._g_data is None and arg._blk is not None:
+                b = arg._blk   # row-sharded matrix: deep copy of this rank's block
+                self._blk = _RowBlock(b.r0, b.r1, b.indptr.clone(), b.indices.clone(), b.data.clone())
+                self._nnz_per_rank = arg._nnz_per_rank
             self._bounds = arg._bounds
             self.indices_sorted = arg.indices_sorted
             self.canonical_format = arg.canonical_format
@@ -226,7 +237,7 @@ class csr_array(CompressedBase):
             return self._h_data.dtype
         from ._device import np_dtype_of
 
-        return np_dtype_of(self._g_data)
+        return np_dtype_of(self._g_data if self._g_data is not None else self._blk.data)
 
     def _cast_data_inplace(self, dtype):
         if self._h_data is not None:
@@ -235,6 +246,12 @@ class csr_array(CompressedBase):
             from ._device import torch_dtype
 
             self._g_data = self._g_data.to(torch_dtype(dtype))
+        if self._h_data is None and self._g_data is None and self._blk is not None:
+            from ._device import torch_dtype
+
+            b = self._blk   # row-sharded: cast the block's values, keep its structure
+            self._blk = _RowBlock(b.r0, b.r1, b.indptr, b.indices, b.data.to(torch_dtype(dtype)))
+            return
         self._blk = None
 
     @classmethod
@@ -248,6 +265,7 @@ class csr_array(CompressedBase):
         self._blk = blk
         self._bounds = bounds
         self._B_full = None
+        self._nnz_per_rank = None
         self.shape = tuple(int(i) for i in shape)
         self._dtype = numpy.dtype(dtype)
         return self
@@ -277,14 +295,53 @@ class csr_array(CompressedBase):
     def _ensure_host(self):
         if self._h_data is None:
             if self._g_data is None:
-                raise RuntimeError(
-                    "this csr_array holds only a local row block (from_row_block); "
-                    "global arrays are not materialised"
-                )
+                # row-sharded matrix (from_row_block / distributed SpGEMM result): the global
+                # arrays are gathered on request — a COLLECTIVE, every rank must get here
+                self._gather_global()
             self._h_data = self._g_data.detach().cpu().numpy()
             self._h_indices = self._g_indices.detach().cpu().numpy().astype(numpy.int64, copy=False)
             self._h_indptr = self._g_indptr.detach().cpu().numpy()
         return self._h_data, self._h_indices, self._h_indptr
+
+    def _gather_global(self):
+        """Materialise the replicated global arrays of a row-sharded matrix on the device:
+        all-gather(v) of the row blocks; the global indptr comes from the per-rank nnz offsets
+        (the reference's ncclAllGather + scan of per-rank nnz, spgemm_csr_csr_csr.cu:43-62).
+        Collective; a no-op when the global arrays already exist."""
+        if self._g_data is not None or self._h_data is not None:
+            return
+        blk = self._blk
+        if blk is None:
+            raise RuntimeError("csr_array holds neither global arrays nor a row block")
+        if dist.world_size() == 1:
+            self._g_data, self._g_indices, self._g_indptr = blk.data, blk.indices, blk.indptr
+            return
+        all_idx, counts = dist.allgather_varlen(blk.indices)
+        all_dat, _ = dist.allgather_varlen(blk.data)
+        row_nnz = blk.indptr[1:] - blk.indptr[:-1]
+        all_row_nnz, _ = dist.allgather_varlen(row_nnz)
+        g_ptr = torch.zeros(self.shape[0] + 1, dtype=torch.int64, device=blk.data.device)
+        torch.cumsum(all_row_nnz, 0, out=g_ptr[1:])
+        self._g_data, self._g_indices, self._g_indptr = all_dat, all_idx, g_ptr
+        self._nnz_per_rank = numpy.asarray(counts, dtype=numpy.int64)
+
+    def gather(self):
+        """Replicate a row-sharded matrix on every rank (collective); returns self."""
+        self._gather_global()
+        return self
+
+    def nnz_offset(self):
+        """Global position of this rank's first stored entry (row-sharded matrices): the exclusive
+        scan of the per-rank nnz, what the reference adds to its local `pos`
+        (spgemm_csr_csr_csr.cu:317-332)."""
+        counts = self._rank_nnz()
+        return int(counts[: dist.rank()].sum())
+
+    def _rank_nnz(self):
+        if getattr(self, "_nnz_per_rank", None) is None:
+            blk = self._block()
+            self._nnz_per_rank = dist.allgather_i64(blk.nnz, blk.data.device)
+        return self._nnz_per_rank
 
     def row_bounds(self):
         if self._bounds is None:
@@ -368,10 +425,8 @@ class csr_array(CompressedBase):
             return int(self._h_data.shape[0])
         if self._g_data is not None:
             return int(self._g_data.numel())
-        # row-block-only matrix: global nnz = sum over ranks
-        t = torch.tensor([self._blk.nnz], dtype=torch.int64, device=self._blk.data.device)
-        dist.allreduce_sum_(t)
-        return int(t.item())
+        # row-sharded matrix: global nnz = sum of the per-rank counts
+        return int(self._rank_nnz().sum())
 
     @property
     def dtype(self):
@@ -449,11 +504,25 @@ class csr_array(CompressedBase):
             return self._h_data.astype(dtype, casting=casting, copy=True)
         from ._device import torch_dtype
 
-        return self._g_data.to(torch_dtype(dtype), copy=True)
+        src = self._g_data if self._g_data is not None else self._blk.data
+        return src.to(torch_dtype(dtype), copy=True)
 
     def _with_data(self, data, copy=True):
         """A different matrix with the same sparsity structure (reference base.py:177-199);
         structure arrays are shared unless ``copy``."""
+        if _is_dev(data) and self._h_data is None and self._g_data is None and self._blk is not None:
+            # row-sharded matrix: `data` are the values of this rank's block
+            from ._device import np_dtype_of
+
+            b = self._blk
+            assert data.numel() == b.nnz
+            ip, idx = (b.indptr.clone(), b.indices.clone()) if copy else (b.indptr, b.indices)
+            out = csr_array._from_parts(self.shape, np_dtype_of(data), bounds=self._bounds,
+                                        blk=_RowBlock(b.r0, b.r1, ip, idx, data.contiguous()))
+            out._nnz_per_rank = self._nnz_per_rank
+            if not copy:
+                out._blk.plan = b.plan
+            return out
         if _is_dev(data):
             from ._device import np_dtype_of, to_device
 
@@ -519,15 +588,37 @@ class csr_array(CompressedBase):
         return to_host(full[:n_out])
 
     def todense(self, order=None, out=None):
-        """Host utility (the reference runs it as a single task, csr.py:383; SURVEY §2 keeps
-        the GPU kernel out of scope).  Duplicates: last one wins (csr_to_dense.cc loop)."""
+        """CSR → dense (reference csr.py:370-383 → CSRToDense task, csr_to_dense.cu:25-47).
+        Duplicates: last one wins (csr_to_dense.cc loop).  Single process with a GPU: the
+        b2s_csr_to_dense kernel fills a device matrix (returned as numpy like every host-facing
+        result, or written into a CUDA tensor ``out``); several ranks / no GPU: assembled on the
+        host from the gathered arrays."""
         if order is not None:
             raise NotImplementedError
+        if out is not None:
+            out_dtype = _torch_np_dtype(out) if isinstance(out, torch.Tensor) else numpy.asarray(out).dtype
+            if out_dtype != self.dtype:
+                raise ValueError(f"Output type {out_dtype} is not consistent with dtype {self.dtype}")
+        if dist.world_size() == 1 and torch.cuda.is_available() and self.shape[0] * self.shape[1] > 0:
+            from ._device import ptr, stream_ptr, to_host, torch_dtype, vt_enum
+
+            blk = self._block()
+            dense = out if (_is_dev(out) and out.is_contiguous()) else torch.empty(
+                self.shape, dtype=torch_dtype(self.dtype), device=blk.data.device)
+            N.check(N.load().b2s_csr_to_dense(vt_enum(self.dtype), blk.itype, self.shape[0], self.shape[1],
+                                              ptr(blk.indptr), ptr(blk.indices), ptr(blk.data), ptr(dense),
+                                              stream_ptr()), "csr_to_dense")
+            if out is None:
+                return to_host(dense)
+            if dense is not out:
+                if isinstance(out, torch.Tensor):
+                    out.copy_(dense)
+                else:
+                    numpy.asarray(out)[...] = to_host(dense)
+            return out
         hd, hi, hp = self._ensure_host()
         if out is not None:
             out = numpy.asarray(out)
-            if out.dtype != self.dtype:
-                raise ValueError(f"Output type {out.dtype} is not consistent with dtype {self.dtype}")
             out[...] = 0
         else:
             out = numpy.zeros(self.shape, dtype=self.dtype)
@@ -684,6 +775,48 @@ def _torch_np_dtype(t):
     return np_dtype_of(t)
 
 
+def _counts_to_csr(nrows, ncols, count_pass, fill_pass, val_dtype, dev):
+    """Shared two-pass shape of the device constructors: count → native scan → (nnz) → fill.
+    Returns device (data, indices, indptr)."""
+    from ._device import ptr, stream_ptr
+
+    lib = N.load()
+    indptr = torch.empty(nrows + 1, dtype=torch.int64, device=dev)
+    count_pass(indptr[1:])
+    ws_bytes = int(lib.b2s_scan_workspace_bytes(nrows))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    N.check(lib.b2s_scan_i64(nrows, ptr(indptr), ptr(ws), ws_bytes, stream_ptr()), "scan_i64")
+    nnz = int(indptr[-1].item())     # the one host sync (the reference blocks on int(nnz) too, csr.py:130)
+    narrow = ncols <= _INT32_MAX and not settings.index64()
+    idx = torch.empty(nnz, dtype=torch.int32 if narrow else torch.int64, device=dev)
+    dat = torch.empty(nnz, dtype=val_dtype, device=dev)
+    if nnz > 0:
+        fill_pass(N.B2S_I32 if narrow else N.B2S_I64, indptr, idx, dat)
+    return dat, idx, indptr
+
+
+def _dense_to_csr_device(dense: torch.Tensor):
+    """Dense CUDA matrix → device CSR arrays (b2s_dense_to_csr_count / _fill)."""
+    from ._device import np_dtype_of, ptr, stream_ptr, vt_enum
+
+    dense = dense.detach()
+    if not dense.is_contiguous():
+        dense = dense.contiguous()
+    nrows, ncols = int(dense.shape[0]), int(dense.shape[1])
+    vt = vt_enum(np_dtype_of(dense))
+    lib = N.load()
+
+    def count(row_nnz):
+        N.check(lib.b2s_dense_to_csr_count(vt, nrows, ncols, ncols, ptr(dense), ptr(row_nnz), stream_ptr()),
+                "dense_to_csr_count")
+
+    def fill(it, indptr, idx, dat):
+        N.check(lib.b2s_dense_to_csr_fill(vt, it, nrows, ncols, ncols, ptr(dense), ptr(indptr), ptr(idx), ptr(dat),
+                                          stream_ptr()), "dense_to_csr_fill")
+
+    return _counts_to_csr(nrows, ncols, count, fill, dense.dtype, dense.device)
+
+
 # ---------------------------------------------------------------------------- SpMV
 def _spmv_block(A: csr_array, blk: _RowBlock, x_dev, y_dev):
     """y_dev[0:blk.nrows] = A[blk.r0:blk.r1, :] @ x_dev   (one native launch sequence)."""
@@ -796,6 +929,8 @@ def _full_device_csr(B: csr_array):
         B._B_full = (blk.indptr, blk.indices, blk.data)
         return B._B_full
     narrow = B._narrow_ok()
+    if B._g_data is None and B._h_data is None:
+        B._gather_global()       # row-sharded B (e.g. the result of an earlier distributed SpGEMM)
     if B._g_data is not None:
         idx = B._g_indices
         if narrow and idx.dtype == torch.int64:
@@ -867,14 +1002,14 @@ def spgemm_csr_csr_csr(A: csr_array, B: csr_array) -> csr_array:
         C = csr_array._from_parts(shape, A.dtype, g=(c_dat, c_idx, c_ptr))
         C._blk = _RowBlock(0, shape[0], c_ptr, c_idx, c_dat)
     else:
-        # replicated C: all-gather(v) of the blocks + global offsets from the per-rank nnz
-        all_idx, counts = dist.allgather_varlen(c_idx)
-        all_dat, _ = dist.allgather_varlen(c_dat)
-        row_nnz = c_ptr[1:] - c_ptr[:-1]
-        all_row_nnz, _ = dist.allgather_varlen(row_nnz)
-        g_ptr = torch.zeros(shape[0] + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(all_row_nnz, 0, out=g_ptr[1:])
-        C = csr_array._from_parts(shape, A.dtype, g=(all_dat, all_idx, g_ptr), bounds=A.row_bounds())
+        # row-sharded C, as upstream (spgemm_csr_csr_csr.cu:43-62,317-332): every rank keeps its row
+        # block; only the per-rank nnz is exchanged (→ global offsets).  The replicated arrays are
+        # gathered on request (C.gather(), C.indices / .data / .indptr, or C as the B of a later A@B).
+        C = csr_array._from_parts(shape, A.dtype, bounds=A.row_bounds(),
+                                  blk=_RowBlock(blk.r0, blk.r1, c_ptr, c_idx, c_dat))
+        C._nnz_per_rank = dist.allgather_i64(int(nnzC.value), dev)
+        prod_all = dist.allgather_i64(int(products.value), dev)
+        products = c_int64(int(prod_all.sum()))
     C.indices_sorted = True
     C._last_products = int(products.value)
     return C

@@ -74,7 +74,59 @@ class dia_array(CompressedBase):
     T = property(transpose)
 
     # ---- DIA → CSR -----------------------------------------------------------------------
+    def _tocsr_device(self):
+        """DIA → CSR on the GPU (b2s_dia_to_csr_count / _fill: one thread per row walks the diagonals
+        by ascending offset, drops explicit zeros — reference dia.py:159-190); the CSR arrays stay on
+        the device."""
+        import torch
+
+        from . import _native as N
+        from ._device import ptr, require_cuda, stream_ptr, torch_dtype, vt_enum
+        from .csr import _counts_to_csr
+
+        dev = require_cuda()
+        rows, cols = self.shape
+        vals = numpy.ascontiguousarray(self._values)
+        ndiag, width = int(vals.shape[0]), int(vals.shape[1])
+        offs = numpy.ascontiguousarray(self._offs, dtype=numpy.int64)
+        order = numpy.argsort(offs, kind="stable").astype(numpy.int32)
+        d_vals = torch.from_numpy(vals).to(dev)
+        d_offs = torch.from_numpy(offs).to(dev)
+        d_order = torch.from_numpy(order).to(dev)
+        vt = vt_enum(self.dtype)
+        lib = N.load()
+
+        def count(row_nnz):
+            N.check(lib.b2s_dia_to_csr_count(vt, rows, cols, ndiag, width, width, ptr(d_vals), ptr(d_offs),
+                                             ptr(d_order), ptr(row_nnz), stream_ptr()), "dia_to_csr_count")
+
+        def fill(it, indptr, idx, dat):
+            N.check(lib.b2s_dia_to_csr_fill(vt, it, rows, cols, ndiag, width, width, ptr(d_vals), ptr(d_offs),
+                                            ptr(d_order), ptr(indptr), ptr(idx), ptr(dat), stream_ptr()),
+                    "dia_to_csr_fill")
+
+        dat, idx, indptr = _counts_to_csr(rows, cols, count, fill, torch_dtype(self.dtype), dev)
+        return csr_array((dat, idx, indptr), shape=self.shape, dtype=self.dtype)
+
     def tocsr(self, copy=False):
+        """With a GPU the conversion runs on the device; the numpy path below serves GPU-less hosts
+        (construction only — every compute entry point still requires the GPU) and is the statement
+        the device kernels are tested against."""
+        import torch
+
+        from ._device import vt_enum
+
+        rows, cols = self.shape
+        if torch.cuda.is_available() and rows > 0 and cols > 0 and self._values.size > 0:
+            try:
+                vt_enum(self.dtype)
+            except NotImplementedError:
+                pass          # integer / bool matrices are representable but not computable: host path
+            else:
+                return self._tocsr_device()
+        return self._tocsr_host()
+
+    def _tocsr_host(self):
         rows, cols = self.shape
         r_parts, c_parts, v_parts = [], [], []
         for d, k in enumerate(self._offs.tolist()):

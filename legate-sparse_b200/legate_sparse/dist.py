@@ -129,6 +129,20 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def allgather_i64(value: int, device=None) -> np.ndarray:
+    """All-gather of one int64 per rank (the reference's ncclAllGather of per-rank nnz,
+    spgemm_csr_csr_csr.cu:43-62); returns the host array of the G values."""
+    G = world_size()
+    if G == 1:
+        return np.array([int(value)], dtype=np.int64)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    cnt = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    cnts = torch.empty(G, dtype=torch.int64, device=device)
+    td.all_gather_into_tensor(cnts, cnt)
+    return cnts.cpu().numpy().astype(np.int64)
+
+
 def allgather_varlen(local: torch.Tensor) -> tuple[torch.Tensor, np.ndarray]:
     """all-gather(v) of 1-D tensors of different lengths: returns (concatenation in rank
     order, per-rank counts).  Used for the SpGEMM C blocks; the count exchange is the

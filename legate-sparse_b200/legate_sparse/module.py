@@ -1,7 +1,7 @@
 """Names exported at package level (same public names as the reference's module.py:40-70)."""
 from . import csr as _csr
 from .dia import dia_array  # noqa: F401
-from .gallery import diags  # noqa: F401
+from .gallery import diags, random  # noqa: F401
 from .io import mmread  # noqa: F401
 from .types import coord_ty, nnz_ty  # noqa: F401
 

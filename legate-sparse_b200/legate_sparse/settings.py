@@ -5,8 +5,10 @@ only kernel-selection switches survive here — the Legate settings machinery is
                               has a single algorithm, so the flag is read and ignored.
   B2S_INDEX64=1               keep 64-bit column indices on the device (default: 32-bit when
                               ncols < 2**31, like scipy).
-  B2S_SPMV_VARIANT=auto|rowvec|tile|pipe|merge   (auto = merge when a plan exists and arrays are aligned)
+  B2S_SPMV_VARIANT=auto|rowvec|tile|pipe   (auto = pipe when a plan exists and the arrays are 16-byte
+                              aligned, else tile, else rowvec)
   B2S_SPMV_TILE_NNZ=1024|2048|4096   (read by the native library)
+  B2S_SPMV_GROUPS=1|2                (read by the native library) consumer groups of the pipe kernel
   B2S_SPMV_NO_WINDOW=1               (read by the native library) disable TMA x-window staging
 """
 import os
@@ -21,7 +23,7 @@ class _Settings:
 
     def spmv_variant(self) -> int:
         v = os.environ.get("B2S_SPMV_VARIANT", "auto").lower()
-        return {"auto": 0, "rowvec": 1, "tile": 2, "pipe": 3, "merge": 4, "wpipe": 5}.get(v, 0)
+        return {"auto": 0, "rowvec": 1, "tile": 2, "pipe": 3}.get(v, 0)
 
 
 settings = _Settings()

@@ -85,11 +85,28 @@ def main():
     assert relerr(W @ xw, bw) < 1e-10
     # --- SpGEMM: row blocks of A x replicated B, C all-gathered(v)
     R = gen.rmat_csr(10)
-    C = sparse.csr_array(R) @ sparse.csr_array(R)
+    Rd = sparse.csr_array(R)
+    C = Rd @ Rd
     E = (R @ R).tocsr()
     E.sort_indices()
+    # C stays ROW-SHARDED (reference spgemm_csr_csr_csr.cu:43-62,317-332): only per-rank nnz travelled
+    assert C._g_data is None and C._h_data is None and C._blk is not None
+    assert C.nnz == E.nnz
+    b0, b1 = int(C.row_bounds()[rank]), int(C.row_bounds()[rank + 1])
+    assert C.nnz_offset() == int(E.indptr[b0]) and C._blk.nnz == int(E.indptr[b1] - E.indptr[b0])
+    # row-sharded C as the A of the next product (no gather), then as its B (gathered on request)
+    C2 = C @ Rd
+    E2 = (E @ R).tocsr(); E2.sort_indices()
+    assert C2.nnz == E2.nnz and C._g_data is None
+    C3 = Rd @ C
+    E3 = (R @ E).tocsr(); E3.sort_indices()
+    assert np.array_equal(C3.indptr, E3.indptr) and np.array_equal(C3.indices, E3.indices)
+    assert relerr(C3.data, E3.data) < 1e-12
+    yC = C @ np.ones(R.shape[0])                      # SpMV with the row-sharded product
+    assert relerr(yC, E @ np.ones(R.shape[0])) < 1e-12
     assert np.array_equal(C.indptr, E.indptr) and np.array_equal(C.indices, E.indices)
     assert relerr(C.data, E.data) < 1e-12
+    assert np.array_equal(C2.indptr, E2.indptr) and relerr(C2.data, E2.data) < 1e-12
     # distributed diagonal
     assert np.allclose(Ad.diagonal(), P.diagonal())
     torch.cuda.synchronize()

@@ -73,6 +73,20 @@ def _worker(rank, world, port, n, seed, q):
         C = sp.csr_array((all_val.numpy(), all_idx.numpy(), gp), shape=(n, n))
         assert int(counts.sum()) == C.nnz
         assert np.allclose(np.asarray(C.todense()), np.asarray((S @ S).todense()), rtol=1e-12, atol=1e-13)
+        # (e) the product's row-sharded result object: per-rank nnz exchange (reference
+        # spgemm_csr_csr_csr.cu:43-62), global offset of the block, gather on request
+        from legate_sparse.csr import _RowBlock, csr_array
+
+        blkC = _RowBlock(r0, r1, torch.from_numpy(cp.astype(np.int64)), torch.from_numpy(ci.astype(np.int64)),
+                         torch.from_numpy(cv))
+        Cs = csr_array._from_parts((n, n), np.float64, bounds=np.asarray(bounds, dtype=np.int64), blk=blkC)
+        assert Cs._g_data is None and Cs._h_data is None      # nothing replicated yet
+        assert Cs.nnz == C.nnz
+        assert Cs.nnz_offset() == int(counts[:rank].sum())
+        Cc = Cs.copy()                                        # deep copy of a row-sharded matrix
+        assert Cc._blk is not Cs._blk and Cc.dtype == Cs.dtype
+        assert np.array_equal(Cs.indptr, gp) and np.array_equal(Cs.indices, all_idx.numpy())
+        assert np.array_equal(Cs.data, all_val.numpy())
         q.put((rank, "ok"))
     except Exception as e:  # surface the failure to the parent
         import traceback

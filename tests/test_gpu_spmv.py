@@ -50,7 +50,7 @@ def test_spmv_golden_fixture():
     assert np.array_equal(T @ np.ones(5), np.array(k["A_ones"], dtype=float))
 
 
-@pytest.mark.parametrize("variant", ["rowvec", "tile", "pipe", "merge"])
+@pytest.mark.parametrize("variant", ["rowvec", "tile", "pipe"])
 @pytest.mark.parametrize("index64", ["0", "1"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
 def test_spmv_variants_types(monkeypatch, variant, index64, dtype):
@@ -71,11 +71,15 @@ def test_spmv_variants_types(monkeypatch, variant, index64, dtype):
     assert relerr(y, S @ x) < tol
 
 
+@pytest.mark.parametrize("groups,tile", [("1", "1024"), ("1", "2048"), ("2", "1024"), ("2", "2048")])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
-def test_spmv_wpipe_variant(monkeypatch, dtype):
-    """warp-autonomous TMA kernel (needs a 1024-nnz plan): irregular rows, empty rows, long rows"""
-    monkeypatch.setenv("B2S_SPMV_VARIANT", "wpipe")
-    monkeypatch.setenv("B2S_SPMV_TILE_NNZ", "1024")
+def test_spmv_pipe_groups_irregular_rows(monkeypatch, dtype, groups, tile):
+    """products consumer of the TMA pipe kernel, one group or two ping-pong groups, both tile
+    sizes: irregular rows, empty rows, rows longer than a tile"""
+    monkeypatch.setenv("B2S_SPMV_VARIANT", "pipe")
+    monkeypatch.setenv("B2S_SPMV_GROUPS", groups)
+    monkeypatch.setenv("B2S_SPMV_TILE_NNZ", tile)
+    monkeypatch.setenv("B2S_SPMV_NO_WINDOW", "1")
     rng = np.random.default_rng(12)
     n, m = 4000, 3500
     deg = rng.integers(0, 12, size=n)
@@ -98,7 +102,7 @@ def test_spmv_wpipe_variant(monkeypatch, dtype):
     y = A @ x
     tol = 1e-10 if np.dtype(dtype) != np.float32 else 3e-5
     assert relerr(y, S @ x) < tol
-    assert A._block().plan.info()["tile_nnz"] == 1024
+    assert A._block().plan.info()["tile_nnz"] == int(tile)
 
 
 def _check(A_sp, seed=1, tol=1e-10):

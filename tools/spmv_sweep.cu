@@ -98,6 +98,7 @@ double run_case(const char* name, b2s_itype it, int64_t n, int64_t m, int64_t nn
                 const I* cols, const double* vals, const double* x, double* y, int variant, int tile, int iters,
                 bool nowin) {
   if (tile) { char buf[32]; snprintf(buf, sizeof buf, "%d", tile); setenv("B2S_SPMV_TILE_NNZ", buf, 1); }
+  else if (!getenv("SWEEP_COLBLOCK")) unsetenv("B2S_SPMV_TILE_NNZ");
   if (getenv("SWEEP_COLBLOCK")) {   // column-blocked operand: SWEEP_COLBLOCK=N blocks (0 = library heuristic)
     int nb = atoi(getenv("SWEEP_COLBLOCK"));
     if (nb == 0) {
@@ -201,10 +202,10 @@ int main(int argc, char** argv) {
   fill_x<<<(unsigned)((m + 255) / 256), 256>>>(m, x);
   CK(cudaDeviceSynchronize());
 
-  // single-config mode (for ncu): spmv_sweep n k iters mode single <variant 1|2|3> <tile> <stages> [i64]
+  // single-config mode (for ncu): spmv_sweep n k iters mode single <variant 1|2|3> <tile> <groups> [i64]
   if (argc > 8 && std::string(argv[5]) == "single") {
     int variant = atoi(argv[6]), tile = atoi(argv[7]);
-    setenv("B2S_SPMV_STAGES", argv[8], 1);
+    setenv("B2S_SPMV_GROUPS", argv[8], 1);
     bool i64 = argc > 9 && std::string(argv[9]) == "i64";
     if (i64) run_case<int64_t>("single", B2S_I64, n, m, nnz, indptr, c64, vals, x, y, variant, tile, iters, false);
     else     run_case<int32_t>("single", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, variant, tile, iters, false);
@@ -225,24 +226,24 @@ int main(int argc, char** argv) {
     printf("ceiling gather (col32 + x[col])       : %8.3f ms  %7.1f Ggather/s\n", ms, nnz / ms / 1e6);
     CK(cudaDeviceSynchronize());
   }
+  if (getenv("SWEEP_COLBLOCK")) {   // column-blocked operand: one measurement with the current environment
+    run_case<int32_t>("colblock", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_PIPE, 0, iters, false);
+    return 0;
+  }
   int tiles[2] = {1024, 2048};
-  const char* stg[3] = {"2", "3", "4"};
-  const int variants[2] = {4, 3};
-  const char* vname[2] = {"merge", "pipe"};
-  for (int vi = 0; vi < 2; ++vi)
-    for (int ti = 0; ti < 2; ++ti)
-      for (int si = 0; si < 3; ++si) {
-        setenv("B2S_SPMV_STAGES", stg[si], 1);
-        char nm[64]; snprintf(nm, sizeof nm, "%s stages=%s", vname[vi], stg[si]);
-        run_case<int32_t>(nm, B2S_I32, n, m, nnz, indptr, c32, vals, x, y, variants[vi], tiles[ti], iters, false);
-        if (mode == "banded") {
-          snprintf(nm, sizeof nm, "%s stages=%s (no x window)", vname[vi], stg[si]);
-          run_case<int32_t>(nm, B2S_I32, n, m, nnz, indptr, c32, vals, x, y, variants[vi], tiles[ti], iters, true);
-        }
+  const char* grp[2] = {"1", "2"};
+  for (int gi = 0; gi < 2; ++gi)
+    for (int ti = 0; ti < 2; ++ti) {
+      setenv("B2S_SPMV_GROUPS", grp[gi], 1);
+      char nm[64]; snprintf(nm, sizeof nm, "pipe groups=%s", grp[gi]);
+      run_case<int32_t>(nm, B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_PIPE, tiles[ti], iters, false);
+      if (mode == "banded") {
+        snprintf(nm, sizeof nm, "pipe groups=%s (no x window)", grp[gi]);
+        run_case<int32_t>(nm, B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_PIPE, tiles[ti], iters, true);
       }
-  setenv("B2S_SPMV_STAGES", "2", 1);
-  run_case<int64_t>("merge stages=2", B2S_I64, n, m, nnz, indptr, c64, vals, x, y, 4, 1024, iters, false);
-  run_case<int64_t>("merge stages=2", B2S_I64, n, m, nnz, indptr, c64, vals, x, y, 4, 2048, iters, false);
+    }
+  unsetenv("B2S_SPMV_GROUPS");
+  run_case<int64_t>("pipe", B2S_I64, n, m, nnz, indptr, c64, vals, x, y, B2S_SPMV_PIPE, 2048, iters, false);
   run_case<int32_t>("tile", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_TILE, 1024, iters, true);
   run_case<int32_t>("rowvec", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_ROWVEC, 0, iters, false);
   return 0;
