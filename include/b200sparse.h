@@ -218,6 +218,22 @@ int b2s_vscale_inv(b2s_dtype vt, int64_t n, const void* x, const void* s, void* 
                    b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Cross-GPU all-reduce(sum) of one device scalar per rank through peer-mapped "boards" (NVLink P2P
+ * stores + sequence flags inside a one-warp kernel; summed in rank order → bit-identical on every
+ * rank).  The CG iteration's replacement for NCCL all-reduces of rho / p.q — the reference reduces
+ * the same scalars as Legate futures (legate_sparse/linalg.py:519-526).
+ *   boards[g]    device address of rank g's board (b2s_board_bytes() bytes, zero-initialised,
+ *                symmetric memory; own board included)
+ *   seq_counters >= 4 local device uint64, zeroed once;  err: optional local device int, set when
+ *                a peer does not answer within ~8 s (the kernel never hangs)
+ *   cur_out/prev_out (optional): prev_out[0] = cur_out[0]; cur_out[0] = sum
+ * ---------------------------------------------------------------------- */
+int64_t b2s_board_bytes(void);
+int b2s_allreduce_board(b2s_dtype vt, void* inout, void* const* boards, int rank, int nranks,
+                        int channel, void* seq_counters, void* cur_out, void* prev_out, void* err,
+                        b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * CSR x CSR SpGEMM  C = A B.   replaces SpGEMMCSRxCSRxCSRGPU
  *   src/sparse/array/csr/spgemm_csr_csr_csr.cu:64-487 (cuSPARSE SpGEMM) and the
  *   two-task CPU shape (NNZ task + numeric task, csr.py:687-744,

@@ -35,6 +35,7 @@ struct PlanHeader {  // host-side plan object
   void*    head;       // [ntiles] * 16 bytes
   void*    dotp;       // [ntiles] * 16 bytes (per-tile partials of the fused dot)
   int64_t  empty_rows; // number of rows without non-zeros
+  int64_t  max_row;    // longest row (nnz) — selects the long-row pass of the products consumer
   int64_t* counters;   // [4]
 };
 
@@ -108,11 +109,20 @@ __global__ void plan_tile_window_kernel(int64_t nnz, int64_t ntiles, int64_t til
 
 __global__ void plan_count_empty_kernel(int64_t nrows, const int64_t* __restrict__ indptr,
                                         int64_t* __restrict__ counters) {
-  int64_t cnt = 0;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x)
-    cnt += (indptr[r + 1] == indptr[r]);
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd((unsigned long long*)&counters[2], (unsigned long long)cnt);
+  int64_t cnt = 0, mx = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t len = indptr[r + 1] - indptr[r];
+    cnt += (len == 0);
+    mx = max(mx, len);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) atomicAdd((unsigned long long*)&counters[2], (unsigned long long)cnt);
+    if (mx) atomicMax((unsigned long long*)&counters[3], (unsigned long long)mx);
+  }
 }
 
 // ------------------------------------------------------------------ helpers
@@ -352,13 +362,13 @@ static int env_int(const char* name, int dflt) {
 //   B2S_SPMV_GROUPS   1 | 2      consumer groups per CTA (default 2: ping-pong)
 static int pipe_groups_default() { int g = env_int("B2S_SPMV_GROUPS", 2); return g == 1 ? 1 : 2; }
 
-template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG>
+template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG, bool LONGROWS = false>
 static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
                             const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
   using L = PipeLayout<V, I, TILE>;
   const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
-  auto kern = spmv_pipe_kernel<V, I, TILE, STAGES, WINDOW, DOT, BCAST, NG>;
+  auto kern = spmv_pipe_kernel<V, I, TILE, STAGES, WINDOW, DOT, BCAST, NG, LONGROWS>;
   // function attributes are per device: cache the resident-CTA count per (instantiation, device)
   static std::atomic<int> blocks_per_sm[kMaxDevices];
   const int dev = current_device();
@@ -402,6 +412,15 @@ static int launch_pipe_tile(const PlanHeader* P, const int64_t* indptr, const I*
   const bool bcast = peers.n != 0;
 #define B2S_PIPE(S, W, B, G) launch_pipe_inst<V, I, TILE, S, W, DOT, B, G>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, accumulate, st)
   if (window) return bcast ? B2S_PIPE(2, true, true, 1) : B2S_PIPE(2, true, false, 1);
+  // skewed row lengths (power-law): a row much longer than the tile average would be summed by one
+  // small lane group — give those rows a warp each in a second pass (plain SpMV instances only)
+  bool longrows = P->max_row > 64 && P->max_row * P->nrows > 8 * P->nnz;
+  longrows = env_int("B2S_SPMV_LONGROWS", longrows ? 1 : 0) != 0;
+  if constexpr (!DOT && TILE == 1024) {
+    if (longrows && !bcast)
+      return launch_pipe_inst<V, I, TILE, 4, false, false, false, 2, true>(P, indptr, cols, vals, x, y, dot_partials, w,
+                                                                          npartials, peers, accumulate, st);
+  }
   if (pipe_groups_default() == 2) {
     if constexpr (TILE == 1024) return bcast ? B2S_PIPE(4, false, true, 2) : B2S_PIPE(4, false, false, 2);
     else                        return bcast ? B2S_PIPE(2, false, true, 2) : B2S_PIPE(2, false, false, 2);
@@ -619,7 +638,7 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
     P->tile_win = reinterpret_cast<int64_t*>(base);               base += nt * 16;
     P->head = reinterpret_cast<void*>(base);                      base += nt * 16;
     P->dotp = reinterpret_cast<void*>(base);                      base += nt * 16;
-    P->empty_rows = 0;
+    P->empty_rows = 0; P->max_row = 0;
     if (nt == 0) break;
     cudaError_t e = cudaMemsetAsync(P->counters, 0, 64, st);
     if (e != cudaSuccess) { delete P; set_error("memset failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
@@ -640,14 +659,15 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
       plan_count_empty_kernel<<<(unsigned)blocks, 256, 0, st>>>(nrows, indptr, P->counters);
       g_launch_count.fetch_add(1);
     }
-    int64_t h[3] = {0, 0, 0};
+    int64_t h[4] = {0, 0, 0, 0};
     e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 24, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 32, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { delete P; set_error("plan build failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
     P->window_tiles = h[0];
     P->head_tiles = h[1];
     P->empty_rows = h[2];
+    P->max_row = h[3];
     if (forced || P->window_tiles * 2 >= P->ntiles) break;   // keep this tiling
   }
   *out_plan = P;

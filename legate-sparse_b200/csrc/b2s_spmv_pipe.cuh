@@ -82,7 +82,11 @@ template <typename I, int C> struct alignas((sizeof(I) * C) < 16 ? (sizeof(I) * 
 // faster and are not instantiated).  BCAST compiles the peer stores in; the plain instances carry
 // no trace of them (the peer ranges cost the banded kernel 13% when they were a runtime branch).
 // NG = consumer groups of the products consumer (1 or 2; STAGES must be a multiple of NG).
-template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG>
+// LONGROWS (products consumer, skewed row lengths — power-law matrices): rows of the tile longer than
+// 32 x (lanes per row) are not summed by their small lane group (one lane walking a 1000-entry row
+// stalls its whole group at the next barrier: 41 % barrier stalls on BASELINE config 5) but
+// deferred to a second pass where each gets a full warp.
+template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG, bool LONGROWS = false>
 __global__ void __launch_bounds__(kPipeThreads)
 spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const int64_t* __restrict__ indptr, const I* __restrict__ cols,
@@ -100,11 +104,15 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + STAGE * STAGES);
   uint64_t* empty_bar = full_bar + STAGES;
   __shared__ V wsum[kPipeConsumers / 32];  // DOT only
+  constexpr int LRCAP = LONGROWS ? TILE / 32 + 2 : 1;
+  __shared__ int lr_count[NG][2];
+  __shared__ int lr_list[NG][2][LRCAP];     // deferred rows (index inside the tile), per group and tile parity
 
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ROWWALK ? kPipeConsumers : GT); }
     fence_mbar_init();
+    for (int g = 0; g < NG; ++g) { lr_count[g][0] = 0; lr_count[g][1] = 0; }
   }
   __syncthreads();
 
@@ -251,6 +259,18 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         }
       }
       if constexpr (NG == 1) consumer_bar_sync(); else group_bar_sync<GT>(grp);
+      const int slot = (int)((i / NG) & 1);
+      if (LONGROWS && gtid == 0) lr_count[grp][slot ^ 1] = 0;   // every warp of the group left the previous tile
+      auto finish_row = [&](int64_t r, int64_t lo_g, V sum, V yold) {
+        bool wrote = false;
+        if (lo_g < S) { head[t] = sum; wrote = true; }
+        else if (r < r_last || lo_g < E) {
+          if (accumulate) sum = vadd(sum, yold);   // y += A_b x : later column blocks
+          if constexpr (BCAST) store_bcast(y, peers, r, sum); else y[r] = sum;
+          wrote = true;
+        }
+        if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
+      };
       for (int64_t base = 0; base < nr; base += groups) {
         const int64_t r = r_begin + base + gtid / lanes;
         const bool valid = (base + gtid / lanes < nr) && (r < nrows);
@@ -259,7 +279,14 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           if (meta.rows_staged) { lo_g = srptr[r - meta.ra]; hi_g = srptr[r - meta.ra + 1]; }
           else                  { lo_g = indptr[r];          hi_g = indptr[r + 1]; }
         }
-        const int lo = (int)(max(lo_g, S) - S), hi = (int)(min(hi_g, E) - S);
+        const int lo = (int)(max(lo_g, S) - S);
+        int hi = (int)(min(hi_g, E) - S);
+        bool defer = false;
+        if (LONGROWS && lanes < 32 && hi - lo > 32 * lanes) {   // uniform over the lane group
+          defer = true;
+          if (gl == 0) lr_list[grp][slot][atomicAdd(&lr_count[grp][slot], 1)] = (int)(base + gtid / lanes);
+          hi = lo;   // nothing to add here; every lane still takes part in the shuffles below
+        }
         V s0 = zero_of<V>(), s1 = zero_of<V>();
         int p = lo + gl;
         for (; p + 3 * lanes < hi; p += 4 * lanes) {   // 4 loads in flight, 2 accumulators
@@ -268,16 +295,29 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           s1 = vadd(s1, vadd(a1, a3));
         }
         for (; p < hi; p += lanes) s0 = vadd(s0, svals[p]);
-        V sum = group_reduce(vadd(s0, s1), lanes);
-        if (valid && gl == 0) {
-          bool wrote = false;
-          if (lo_g < S) { head[t] = sum; wrote = true; }
-          else if (r < r_last || lo_g < E) {
-            if (accumulate) sum = vadd(sum, base == 0 ? ypre : y[r]);   // y += A_b x : later column blocks
-            if constexpr (BCAST) store_bcast(y, peers, r, sum); else y[r] = sum;
-            wrote = true;
+        const V sum = group_reduce(vadd(s0, s1), lanes);
+        if (valid && gl == 0 && !defer) finish_row(r, lo_g, sum, (accumulate && base != 0) ? y[r] : ypre);
+      }
+      if constexpr (LONGROWS) {
+        if constexpr (NG == 1) consumer_bar_sync(); else group_bar_sync<GT>(grp);   // the list of this tile is complete
+        const int nlong = lr_count[grp][slot];
+        const int wid = gtid >> 5, lane = gtid & 31;
+        for (int e = wid; e < nlong; e += GT / 32) {
+          const int64_t r = r_begin + lr_list[grp][slot][e];
+          int64_t lo_g, hi_g;
+          if (meta.rows_staged) { lo_g = srptr[r - meta.ra]; hi_g = srptr[r - meta.ra + 1]; }
+          else                  { lo_g = indptr[r];          hi_g = indptr[r + 1]; }
+          const int lo = (int)(max(lo_g, S) - S), hi = (int)(min(hi_g, E) - S);
+          V s0 = zero_of<V>(), s1 = zero_of<V>();
+          int p = lo + lane;
+          for (; p + 96 < hi; p += 128) {
+            const V a0 = svals[p], a1 = svals[p + 32], a2 = svals[p + 64], a3 = svals[p + 96];
+            s0 = vadd(s0, vadd(a0, a2));
+            s1 = vadd(s1, vadd(a1, a3));
           }
-          if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
+          for (; p < hi; p += 32) s0 = vadd(s0, svals[p]);
+          const V sum = group_reduce(vadd(s0, s1), 32);
+          if (lane == 0) finish_row(r, lo_g, sum, accumulate ? y[r] : zero_of<V>());
         }
       }
       fence_proxy_async_smem();

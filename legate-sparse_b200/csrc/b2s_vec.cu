@@ -356,3 +356,100 @@ extern "C" int b2s_cg_pupdate_halo(b2s_dtype vt, int64_t n, void* p, const void*
   B2S_REQUIRE(npeers == 0 || (lo && hi), "null range arrays");
   return cg_pupdate_impl(vt, n, p, r, rho, rho1, p_peers, npeers, lo, hi, stream);
 }
+
+// =================================================================== cross-GPU scalar exchange
+// All-reduce(sum) of ONE device scalar per rank without NCCL: every rank owns a small "board" in
+// symmetric (peer-mapped) memory; a one-warp kernel stores its partial + a sequence number into its
+// slot of EVERY rank's board (NVLink P2P stores, st.release.sys), spins until the G slots of its own
+// board carry the current sequence number (ld.acquire.sys) and adds them up IN RANK ORDER — the
+// result is bit-identical on every rank and from run to run.  Slots are double-buffered by the
+// parity of the sequence number: a rank can be at most one exchange ahead of a peer on a channel.
+// This is the CG iteration's replacement for two 1-element NCCL all-reduces and a barrier
+// (reference linalg.py:519-526 gets the same values from Legate future reductions).
+namespace b2s {
+
+constexpr int kBoardChannels = 4;
+constexpr int kBoardRanks    = kMaxPeers + 1;
+struct alignas(32) BoardSlot {
+  unsigned char value[16];
+  unsigned long long seq;
+  unsigned long long pad;
+};
+struct BoardPtrs { BoardSlot* b[kBoardRanks]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// inout[0]: this rank's partial on entry, the global sum on exit.  prev_out (optional):
+// prev_out[0] = cur_out[0]; cur_out[0] = sum  (CG: rho1 <- rho, rho <- rr) — saves two copy kernels.
+template <typename V>
+__global__ void __launch_bounds__(32)
+allreduce_board_kernel(V* __restrict__ inout, const BoardPtrs boards, int rank, int nranks, int channel,
+                       unsigned long long* __restrict__ seq_counters, V* __restrict__ cur_out,
+                       V* __restrict__ prev_out, int* __restrict__ err) {
+  __shared__ V vals[kBoardRanks];
+  const int t = threadIdx.x;
+  const unsigned long long seq = seq_counters[channel] + 1ull;
+  const int slot_base = (channel * 2 + (int)(seq & 1ull)) * kBoardRanks;
+  if (t < nranks) {
+    const V mine = inout[0];
+    BoardSlot* dst = boards.b[t] + slot_base + rank;          // my slot on rank t's board
+    *reinterpret_cast<V*>(dst->value) = mine;
+    st_release_sys(&dst->seq, seq);                           // value first, then the flag
+    BoardSlot* src = boards.b[rank] + slot_base + t;           // rank t's slot on my board
+    const long long t0 = clock64();
+    bool ok = true;
+    while (ld_acquire_sys(&src->seq) != seq) {
+      if (clock64() - t0 > (1ll << 34)) { ok = false; break; }   // ~8 s: a peer died — do not hang the GPU
+    }
+    if (!ok && err) atomicExch(err, 1);
+    vals[t] = *reinterpret_cast<const V*>(src->value);   // ordered after the acquire load above
+  }
+  __syncwarp();
+  if (t == 0) {
+    V tot = vals[0];
+    for (int g = 1; g < nranks; ++g) tot = vadd(tot, vals[g]);
+    inout[0] = tot;
+    if (prev_out) prev_out[0] = cur_out[0];
+    if (cur_out) cur_out[0] = tot;
+    seq_counters[channel] = seq;
+  }
+}
+
+}  // namespace b2s
+
+extern "C" int64_t b2s_board_bytes(void) {
+  return (int64_t)sizeof(b2s::BoardSlot) * b2s::kBoardChannels * 2 * b2s::kBoardRanks;
+}
+
+// boards[g] = device address of rank g's board (own board included), all zero-initialised and
+// mapped into this process (symmetric memory).  seq_counters: >= 4 local device uint64, zeroed once;
+// err: optional local device int set when a peer never answers.  Every rank must call with the same
+// channel sequence.  inout is a 1-element device array of dtype vt.
+extern "C" int b2s_allreduce_board(b2s_dtype vt, void* inout, void* const* boards, int rank, int nranks,
+                                   int channel, void* seq_counters, void* cur_out, void* prev_out, void* err,
+                                   b2s_stream_t stream) {
+  B2S_REQUIRE(nranks >= 1 && nranks <= kBoardRanks && rank >= 0 && rank < nranks, "bad rank / nranks");
+  B2S_REQUIRE(channel >= 0 && channel < kBoardChannels, "bad channel");
+  B2S_REQUIRE(inout && boards && seq_counters, "null pointer");
+  B2S_REQUIRE((prev_out == nullptr) || (cur_out != nullptr), "prev_out needs cur_out");
+  BoardPtrs bp{};
+  for (int g = 0; g < nranks; ++g) {
+    B2S_REQUIRE(boards[g] != nullptr, "null board pointer");
+    bp.b[g] = reinterpret_cast<BoardSlot*>(boards[g]);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  B2S_DISPATCH_VT(vt, V, {
+    allreduce_board_kernel<V><<<1, 32, 0, st>>>((V*)inout, bp, rank, nranks, channel,
+                                                (unsigned long long*)seq_counters, (V*)cur_out, (V*)prev_out,
+                                                (int*)err);
+    B2S_CHECK_LAUNCH();
+  });
+  return B2S_OK;
+}

@@ -129,6 +129,11 @@ def zeros(n, dtype) -> torch.Tensor:
 _red_ws = {}
 
 
+def new_reduce_ws() -> torch.Tensor:
+    """A reduction workspace owned by the caller (e.g. one per captured CUDA graph)."""
+    return torch.zeros(int(N.load().b2s_reduce_workspace_bytes()), dtype=torch.uint8, device=require_cuda())
+
+
 def reduce_ws() -> torch.Tensor:
     dev = require_cuda()
     key = (dev.index, torch.cuda.current_stream().cuda_stream)
@@ -249,6 +254,10 @@ class ColBlock:
         x_dev.record_stream(side)
         return x_dev
 
+    def spmv_part(self, b, x, y):
+        """one column block of the sequence (block b only reads slice b of x)"""
+        N.check(self._lib.b2s_spmv_colblock_part(self.handle, b, ptr(x), ptr(y), stream_ptr()), "spmv_colblock_part")
+
     def __del__(self):
         try:
             if self.handle:
@@ -256,6 +265,83 @@ class ColBlock:
                 self.handle = c_void_p(0)
         except Exception:
             pass
+
+
+class HostPipe:
+    """y_host = A x_host for a column-blocked operand, pipelined over PCIe in both directions.
+
+    The row block is cut into `nchunks` row chunks, each with its own column-blocked operand
+    (2-D blocks: row chunk x column block).  Slice b of x is uploaded on a copy stream while earlier
+    blocks run; the launches are ordered so that a row chunk is FINISHED (all its column blocks
+    done) as early as possible, and its rows of y travel back on a second copy stream while the
+    next chunks are still being computed.  Built once per matrix (holds a second column-blocked
+    copy of the values, like ColBlock)."""
+
+    def __init__(self, vt, it, nrows, ncols, indptr, indices, data, nblocks, nchunks):
+        self.nrows, self.ncols, self.nblocks = nrows, ncols, nblocks
+        nchunks = max(1, min(int(nchunks), nrows))
+        step = -(-nrows // nchunks)
+        step += step & 1                      # even chunk starts keep y slices 16-byte aligned
+        self.bounds = [min(i * step, nrows) for i in range(nchunks + 1)]
+        while len(self.bounds) > 2 and self.bounds[-2] == self.bounds[-1]:
+            self.bounds.pop()
+        self.chunks = []
+        ip_host = None
+        for c in range(len(self.bounds) - 1):
+            c0, c1 = self.bounds[c], self.bounds[c + 1]
+            lo, hi = int(indptr[c0].item()), int(indptr[c1].item())
+            ip = (indptr[c0:c1 + 1] - lo).contiguous()
+            cb = ColBlock(vt, it, c1 - c0, ncols, hi - lo, ip, indices[lo:hi], data[lo:hi], nblocks) if hi > lo else None
+            self.chunks.append((c0, c1, ip, cb))
+        info = next(cb.info() for (_, _, _, cb) in self.chunks if cb is not None)
+        self.block_cols = info["block_cols"]
+        dev = indptr.device
+        self.x_dev = torch.empty(ncols, dtype=data.dtype, device=dev)
+        self.y_dev = torch.empty(nrows, dtype=data.dtype, device=dev)
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        # launch order: chunk c / block b at key c + b * lag; ties finish chunks first
+        nc = len(self.chunks)
+        lag = max(1, nc // nblocks)
+        self.order = sorted(((c, b) for c in range(nc) for b in range(nblocks)),
+                            key=lambda cb_: (cb_[0] + cb_[1] * lag, -cb_[1]))
+
+    def run(self, x_host: torch.Tensor, y_host: torch.Tensor):
+        cur = torch.cuda.current_stream()
+        self.h2d.wait_stream(cur)          # earlier readers of x_dev / y_dev are done
+        self.d2h.wait_stream(cur)
+        bw, nb = self.block_cols, self.nblocks
+        ev_x = []
+        with torch.cuda.stream(self.h2d):
+            for b in range(nb):
+                lo, hi = b * bw, min((b + 1) * bw, self.ncols)
+                if hi > lo:
+                    self.x_dev[lo:hi].copy_(x_host[lo:hi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self.h2d)
+                ev_x.append(e)
+        waited = [False] * nb
+        done_blocks = [0] * len(self.chunks)
+        for (c, b) in self.order:
+            c0, c1, _, cb = self.chunks[c]
+            if not waited[b]:
+                cur.wait_event(ev_x[b])
+                waited[b] = True
+            y_c = self.y_dev[c0:c1]
+            if cb is None:
+                if b == 0:
+                    y_c.zero_()
+            else:
+                cb.spmv_part(b, self.x_dev, y_c)
+            done_blocks[c] += 1
+            if done_blocks[c] == nb:       # chunk finished: its rows of y go home
+                e = torch.cuda.Event()
+                e.record(cur)
+                self.d2h.wait_event(e)
+                with torch.cuda.stream(self.d2h):
+                    y_host[c0:c1].copy_(y_c, non_blocking=True)
+        cur.wait_stream(self.d2h)          # the caller's stream order covers the copies
+        return y_host
 
 
 # ------------------------------------------------------------------ typed wrappers
@@ -339,13 +425,13 @@ def axpby(y, x, a, b, isalpha, negate):
     )
 
 
-def dot(x, y, conj=False, out=None):
+def dot(x, y, conj=False, out=None, ws=None):
     dt = np_dtype_of(x)
     if out is None:
         out = empty(1, dt)
     N.check(
-        N.load().b2s_dot(vt_enum(dt), x.numel(), ptr(x), ptr(y), int(conj), ptr(out), ptr(reduce_ws()),
-                         stream_ptr()),
+        N.load().b2s_dot(vt_enum(dt), x.numel(), ptr(x), ptr(y), int(conj), ptr(out),
+                         ptr(ws if ws is not None else reduce_ws()), stream_ptr()),
         "dot",
     )
     return out
@@ -396,11 +482,11 @@ def vscale_inv(x, s, out):
     return out
 
 
-def cg_update(x, r, p, q, rho, pq, rr_out):
+def cg_update(x, r, p, q, rho, pq, rr_out, ws=None):
     dt = np_dtype_of(x)
     N.check(
         N.load().b2s_cg_update(vt_enum(dt), x.numel(), ptr(x), ptr(r), ptr(p), ptr(q), ptr(rho), ptr(pq),
-                               ptr(rr_out), ptr(reduce_ws()), stream_ptr()),
+                               ptr(rr_out), ptr(ws if ws is not None else reduce_ws()), stream_ptr()),
         "cg_update",
     )
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     "b2s_cg_pupdate": (c_int, [c_int, _I64, _P, _P, _P, _P, _P]),
     "b2s_cg_pupdate_bcast": (c_int, [c_int, _I64, _P, _P, _P, _P, _P, c_int, _P]),
     "b2s_cg_pupdate_halo": (c_int, [c_int, _I64, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "b2s_board_bytes": (_I64, []),
+    "b2s_allreduce_board": (c_int, [c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "b2s_spgemm_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "b2s_spgemm_symbolic": (
         c_int,

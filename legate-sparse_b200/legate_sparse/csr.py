@@ -57,7 +57,7 @@ def _as_host(x, dtype=None, copy=False):
 class _RowBlock:
     """Device-resident rows [r0, r1) of a matrix: rebased indptr, (narrowed) indices, data."""
 
-    __slots__ = ("r0", "r1", "nnz", "indptr", "indices", "data", "itype", "plan", "colblock", "_colrange")
+    __slots__ = ("r0", "r1", "nnz", "indptr", "indices", "data", "itype", "plan", "colblock", "hostpipe", "_colrange")
 
     def __init__(self, r0, r1, indptr, indices, data):
         self.r0, self.r1 = int(r0), int(r1)
@@ -66,6 +66,7 @@ class _RowBlock:
         self.itype = N.B2S_I32 if indices.dtype == torch.int32 else N.B2S_I64
         self.plan = None
         self.colblock = None   # None: not decided yet, False: not worthwhile, else _device.ColBlock
+        self.hostpipe = None   # _device.HostPipe of the host-vector path (built on first use)
         self._colrange = None
 
     @property
@@ -414,6 +415,21 @@ class csr_array(CompressedBase):
                                             blk.indices, blk.data, nb)
         return blk.colblock or None
 
+    def _hostpipe(self, blk: _RowBlock):
+        """2-D blocked operand + copy streams of the host-vector SpMV path (built on first use)."""
+        hp = getattr(blk, "hostpipe", None)
+        if hp is None:
+            import os
+
+            from ._device import HostPipe, vt_enum
+
+            cb = self._colblock(blk)
+            nchunks = int(os.environ.get("LEGATE_SPARSE_HOSTPIPE_CHUNKS", "8"))
+            hp = HostPipe(vt_enum(self.dtype), blk.itype, blk.nrows, self.shape[1], blk.indptr, blk.indices,
+                          blk.data, cb.nblocks, nchunks)
+            blk.hostpipe = hp
+        return hp
+
     # ------------------------------------------------------------------ properties
     @property
     def dim(self):
@@ -704,11 +720,28 @@ class csr_array(CompressedBase):
             raise NotImplementedError
 
     def dot_local(self, x, out=None):
-        """SpMV on this rank's row block only (y stays row-sharded, no collective) — what the
-        reference's spmv_microbenchmark measures without --repartition.  Device tensors only."""
+        """SpMV on this rank's row block only (y stays row-sharded) — what the reference's
+        spmv_microbenchmark measures without --repartition.  Device tensors: no collective at all.
+        Host x / host out: x is uploaded in 1/G slices + one NVLink all-gather, and only this rank's
+        rows of y come back (out has blk.nrows entries)."""
         from ._device import empty
 
         blk = self._block()
+        if not _is_dev(x):
+            # host x (replicated on every rank's host) → host y block: upload 1/G of x, all-gather it
+            # over NVLink, multiply, read back only this rank's rows
+            if dist.world_size() == 1:
+                return spmv(self, x, out)
+            x_dev = _x_to_device_dist(self, x)
+            y_dev = empty(blk.nrows, self.dtype)
+            _spmv_block(self, blk, x_dev, y_dev)
+            if out is None:
+                return y_dev.cpu().numpy()
+            if isinstance(out, torch.Tensor):
+                out.copy_(y_dev)
+            else:
+                out[...] = y_dev.cpu().numpy()
+            return out
         y = out if out is not None else empty(blk.nrows, self.dtype)
         _spmv_block(self, blk, x, y)
         return y
@@ -818,6 +851,26 @@ def _dense_to_csr_device(dense: torch.Tensor):
 
 
 # ---------------------------------------------------------------------------- SpMV
+def _x_to_device_dist(A: csr_array, x):
+    """Replicated device copy of a HOST x with several ranks: every rank uploads only its 1/G slice
+    over PCIe and the slices are all-gathered over NVLink (one NCCL all-gather) instead of G full
+    uploads of the same vector."""
+    from ._device import empty, torch_dtype
+
+    G, r = dist.world_size(), dist.rank()
+    m = A.shape[1]
+    xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(numpy.ascontiguousarray(x))
+    if xh.dtype != torch_dtype(A.dtype):
+        xh = xh.to(torch_dtype(A.dtype))
+    cb = dist.row_block_bounds(m, G)
+    x_dev = empty(m, A.dtype)
+    c0, c1 = int(cb[r]), int(cb[r + 1])
+    if c1 > c0:
+        x_dev[c0:c1].copy_(xh[c0:c1], non_blocking=True)
+    dist.allgather_into(x_dev, cb)
+    return x_dev
+
+
 def _spmv_block(A: csr_array, blk: _RowBlock, x_dev, y_dev):
     """y_dev[0:blk.nrows] = A[blk.r0:blk.r1, :] @ x_dev   (one native launch sequence)."""
     from ._device import spmv as _spmv, vt_enum
@@ -848,19 +901,28 @@ def spmv(A: csr_array, x, y=None):
     host_io = not _is_dev(x)
     G = dist.world_size()
     n = A.shape[0]
-    piped = False
     if G == 1 and host_io and A._colblock(blk) is not None:
-        # host x + column-blocked operand: copy slice b+1 of x while block b runs
+        # host x and y + column-blocked operand: 2-D (row chunk x column block) pipeline — slice b+1 of
+        # x is uploaded while block b runs, finished row chunks of y travel back while later chunks are
+        # still being computed (_device.HostPipe)
         from ._device import torch_dtype
 
         xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(numpy.ascontiguousarray(x))
-        if xh.dtype == torch_dtype(A.dtype) and xh.dim() == 1 and xh.is_contiguous():
-            y_dev = y if (y is not None and _is_dev(y) and y.is_contiguous()) else empty(n, A.dtype)
-            A._colblock(blk).spmv_from_host(xh, y_dev, A.shape[1])
-            piped = True
-    if piped:
-        pass
-    elif G == 1:
+        y_t = None
+        if y is None:
+            y_t = torch.empty(n, dtype=torch_dtype(A.dtype))
+        elif isinstance(y, torch.Tensor) and not y.is_cuda and y.is_contiguous() and y.dim() == 1:
+            y_t = y
+        elif isinstance(y, numpy.ndarray) and y.flags.c_contiguous and y.ndim == 1:
+            y_t = torch.from_numpy(y)
+        if (y_t is not None and xh.dtype == torch_dtype(A.dtype) and y_t.dtype == xh.dtype and xh.dim() == 1
+                and xh.is_contiguous()):
+            A._hostpipe(blk).run(xh, y_t)
+            torch.cuda.current_stream().synchronize()      # host memory is handed back: copies must be complete
+            if y is not None:
+                return y
+            return y_t.numpy()
+    if G == 1:
         x_dev = to_device(x, dtype=A.dtype)
         if y is not None and _is_dev(y) and y.is_contiguous():
             y_dev = y
@@ -868,17 +930,18 @@ def spmv(A: csr_array, x, y=None):
             y_dev = empty(n, A.dtype)
         _spmv_block(A, blk, x_dev, y_dev)
     else:
-        x_dev = to_device(x, dtype=A.dtype)
+        x_dev = _x_to_device_dist(A, x) if host_io else to_device(x, dtype=A.dtype)
         bounds = A.row_bounds()
         from ._device import torch_dtype
 
-        # collective decision (same on every rank): symmetric memory available or not
-        sv = dist.symm_vector(n, torch_dtype(A.dtype), "spmv_y")
+        # collective decision (same on every rank): symmetric memory available or not.  Two buffers
+        # are used in turn: the closing barrier of call k orders every peer's reads of buffer k%2
+        # (call k-2's result) before anyone writes it again, so no opening barrier is needed.
+        sv = dist.symm_vector_alternating(n, torch_dtype(A.dtype), "spmv_y")
         if sv is not None:
             # fused SpMV + all-gather: y stores go to every rank's replicated buffer over NVLink
             from ._device import spmv_bcast, vt_enum
 
-            sv.barrier()   # peers are done reading the previous content
             local = sv.t[blk.r0 : blk.r1]
             if blk.nnz > 0 and A._colblock(blk) is not None:
                 A._colblock(blk).spmv(x_dev, local, peer_ptrs=sv.peer_ptrs(blk.r0))

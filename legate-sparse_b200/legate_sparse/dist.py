@@ -228,3 +228,93 @@ def symm_vector(n: int, dtype: torch.dtype, tag: str = "y"):
             return None
         _symm_cache[key] = v
     return v
+
+
+_symm_turn: dict = {}
+
+
+def symm_vector_alternating(n: int, dtype: torch.dtype, tag: str):
+    """Two symmetric vectors per (n, dtype, tag) handed out in turn (collective, same order on every
+    rank).  A producer that closes every use with `barrier()` may then write the returned buffer
+    without an opening barrier: before anyone writes buffer b again, every rank has passed the
+    closing barrier of the call in between, which is stream-ordered after its reads of b."""
+    key = (int(n), dtype, tag)
+    turn = 1 - _symm_turn.get(key, 1)
+    _symm_turn[key] = turn
+    return symm_vector(n, dtype, f"{tag}{turn}")
+
+
+class ScalarBoard:
+    """Peer-mapped boards for in-kernel all-reduces of device scalars (b2s_allreduce_board): one
+    small symmetric buffer per rank + local sequence counters.  Replaces NCCL all-reduce /
+    symmetric-memory barriers inside the CG iteration (one one-warp kernel per exchange)."""
+
+    def __init__(self):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _native as N
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nbytes = int(N.load().b2s_board_bytes())
+        self.t = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.t.zero_()
+        self.h = symm.rendezvous(self.t, td.group.WORLD)
+        self.ptrs = [int(q) for q in self.h.buffer_ptrs]
+        self.arr = (ctypes.c_void_p * len(self.ptrs))(*[ctypes.c_void_p(q) for q in self.ptrs])
+        self.seq = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        self.h.barrier(channel=0)        # every board is zeroed before anyone writes a slot
+        torch.cuda.synchronize()
+
+    def allreduce(self, scalar: torch.Tensor, channel: int, cur_out=None, prev_out=None):
+        """scalar[0] <- sum over ranks (in rank order); optionally prev_out[0] <- cur_out[0],
+        cur_out[0] <- sum.  Stream-ordered, capturable in a CUDA graph."""
+        import ctypes
+
+        from . import _native as N
+        from ._device import np_dtype_of, ptr, stream_ptr, vt_enum
+
+        N.check(
+            N.load().b2s_allreduce_board(
+                vt_enum(np_dtype_of(scalar)), ptr(scalar), ctypes.cast(self.arr, ctypes.c_void_p), rank(),
+                world_size(), int(channel), ptr(self.seq), ptr(cur_out), ptr(prev_out), ptr(self.err), stream_ptr()),
+            "allreduce_board")
+        return scalar
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("in-kernel all-reduce timed out waiting for a peer rank")
+
+
+_board = None
+_board_broken = False
+
+
+def scalar_board():
+    """Cached ScalarBoard (collective on first use), or None when peer memory is unavailable /
+    LEGATE_SPARSE_NO_BOARD is set → callers fall back to NCCL all-reduce."""
+    global _board, _board_broken
+    if _board is not None:
+        return _board
+    if _board_broken or world_size() == 1 or world_size() > 8 or not torch.cuda.is_available():
+        return None
+    if os.environ.get("LEGATE_SPARSE_NO_BOARD", "0") not in ("0", "") or os.environ.get("LEGATE_SPARSE_NO_SYMM", "0") not in ("0", ""):
+        return None
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    b = None
+    try:
+        b = ScalarBoard()
+    except Exception as e:  # pragma: no cover - depends on the box
+        import warnings
+
+        warnings.warn(f"scalar board unavailable ({e}); using NCCL all-reduce")
+        ok.zero_()
+    td.all_reduce(ok, op=td.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        _board_broken = True
+        return None
+    _board = b
+    return _board

@@ -371,6 +371,32 @@ def cg(
     return _vec_out(x, b), iters
 
 
+_cg_profile: list = []   # (iterations, device ms) per graph replay of the last solve (LEGATE_SPARSE_CG_PROFILE=1)
+
+
+def _prof_begin(prof):
+    if prof is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(prof, e0, n):
+    if prof is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    prof.append((n, e0, e1))
+
+
+def cg_profile():
+    """[(iterations, device milliseconds)] per CUDA-graph replay of the last fused CG solve that ran
+    with LEGATE_SPARSE_CG_PROFILE=1 (CUDA events on the launching stream)."""
+    torch.cuda.synchronize()
+    return [(n, e0.elapsed_time(e1)) for (n, e0, e1) in _cg_profile]
+
+
 def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, numpy_mode):
     """Identity-preconditioned CG on row-block-local vectors with fused kernels.
 
@@ -437,16 +463,26 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
     rr = D.zeros(1, dtype)
     D.dot(r, r, out=rho)
     dist.allreduce_sum_(rho)
+    # cross-GPU scalar sums: in-kernel exchange through peer-mapped boards (one one-warp kernel each,
+    # summed in rank order) instead of NCCL all-reduces; channel 0 doubles as the "every p block has
+    # landed" barrier.  Per iteration: ONE sync point per dependency, no NCCL node in the graph.
+    board = dist.scalar_board() if (G > 1 and pv is not None) else None
+    token = D.zeros(1, dtype) if board is not None else None
+    red_ws = D.new_reduce_ws()   # owned by this solve: never allocated inside a graph capture
+
     def body():
         """one CG iteration on fixed buffers (capturable in a CUDA graph)"""
         if pv is not None:
-            # no barrier needed before overwriting p_full: the all-reduce of rr at the end of the
+            # no barrier needed before overwriting p_full: the reduction of rr at the end of the
             # previous iteration already orders every rank's SpMV (the reader of p_full) before this point
             if halo is not None:
                 D.cg_pupdate_halo(p_loc, r, rho, rho1, peer_ptrs, halo[0], halo[1])   # boundary slices only
             else:
                 D.cg_pupdate_bcast(p_loc, r, rho, rho1, peer_ptrs)   # p block → every rank (NVLink stores)
-            pv.barrier()                                          # all blocks have landed
+            if board is not None:
+                board.allreduce(token, 0)                         # all blocks have landed (flag exchange)
+            else:
+                pv.barrier()
         else:
             D.cg_pupdate(p_loc, r, rho, rho1)
             if G > 1:
@@ -457,36 +493,80 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
         else:  # empty block
             q.zero_()
             pq.zero_()
-        dist.allreduce_sum_(pq)
-        D.cg_update(x_loc, r, p_loc, q, rho, pq, rr)
-        dist.allreduce_sum_(rr)
-        rho1.copy_(rho)   # old rho → rho1 ; new rho = rr  (z == r)
-        rho.copy_(rr)
+        if board is not None:
+            board.allreduce(pq, 1)
+        else:
+            dist.allreduce_sum_(pq)
+        D.cg_update(x_loc, r, p_loc, q, rho, pq, rr, ws=red_ws)
+        if board is not None:
+            board.allreduce(rr, 2, cur_out=rho, prev_out=rho1)   # rho1 <- rho ; rho <- sum(rr)  (z == r)
+        else:
+            dist.allreduce_sum_(rr)
+            rho1.copy_(rho)   # old rho → rho1 ; new rho = rr  (z == r)
+            rho.copy_(rr)
 
-    # CUDA graph of the iteration body: removes ~10 launches' worth of host time per iteration
-    # (what bounds multi-GPU / small problems).  LEGATE_SPARSE_CG_GRAPH=0 disables it; the collectives
-    # of the body (NCCL all-reduce, symmetric-memory barrier) are captured with it (measured N=1,2).
+    # CUDA graphs of the iteration body: one iteration, and `conv_test_iters` iterations back to back
+    # (between two convergence tests the host has nothing to say, so one replay = 25 iterations and
+    # the loop is insensitive to host-side jitter).  LEGATE_SPARSE_CG_GRAPH=0 disables them; the
+    # collectives of the body are captured with it.
     mode = os.environ.get("LEGATE_SPARSE_CG_GRAPH", "1")
-    graph = None
     want_graph = callback is None and mode != "0"
+    graph1 = graphN = None
+    nper = max(int(conv_test_iters), 1)
+    prof = _cg_profile if os.environ.get("LEGATE_SPARSE_CG_PROFILE", "0") not in ("0", "") else None
+    if prof is not None:
+        prof.clear()
+
+    def capture(times):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(times):
+                body()
+        return g
+
+    def run(k):
+        """advance k iterations with as few launches as possible"""
+        nonlocal graph1, graphN, want_graph
+        done = 0
+        while done < k:
+            if want_graph and graph1 is None and iters + done >= 1:
+                # iteration 0 ran eagerly (lazy allocations, NCCL warm-up); capture now
+                try:
+                    torch.cuda.synchronize()
+                    graph1 = capture(1)
+                    if nper > 1 and maxiter - iters >= 2 * nper:
+                        graphN = capture(nper)
+                except Exception as e:  # pragma: no cover - depends on driver / NCCL capture support
+                    warnings.warn(f"CUDA graph capture of the CG iteration failed ({e}); running eagerly")
+                    graph1 = graphN = None
+                    want_graph = False
+                    torch.cuda.synchronize()
+            if graphN is not None and k - done >= nper:
+                ev = _prof_begin(prof)
+                graphN.replay()
+                _prof_end(prof, ev, nper)
+                done += nper
+            elif graph1 is not None:
+                ev = _prof_begin(prof)
+                graph1.replay()
+                _prof_end(prof, ev, 1)
+                done += 1
+            else:
+                body()
+                done += 1
+
     iters = 0
     while iters < maxiter:
-        if want_graph and graph is None and iters == 1:
-            # iteration 0 ran eagerly (lazy allocations, NCCL warm-up); capture the body now
-            try:
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    body()
-            except Exception as e:  # pragma: no cover - depends on driver / NCCL capture support
-                warnings.warn(f"CUDA graph capture of the CG iteration failed ({e}); running eagerly")
-                graph, want_graph = None, False
-                torch.cuda.synchronize()
-        if graph is not None:
-            graph.replay()
+        if callback is not None:
+            step = 1
         else:
-            body()
-        iters += 1
+            # iterations until the next convergence test (every conv_test_iters and at maxiter-1)
+            step = nper - iters % nper
+            if iters < maxiter - 1:
+                step = min(step, maxiter - 1 - iters)
+            step = max(1, min(step, maxiter - iters))
+        run(step)
+        iters += step
         if callback is not None:
             xf = dist.allgather_rows(x_loc, bounds) if G > 1 else x_loc
             callback(D.to_host(xf) if numpy_mode else xf)
@@ -499,6 +579,8 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
                 rnorm = float(torch.sqrt(rho.abs()).item())
             if rnorm < atol:
                 break
+    if board is not None:
+        board.check()
     x_out = dist.allgather_rows(x_loc, bounds) if G > 1 else x_loc
     return x_out, iters
 

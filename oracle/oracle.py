@@ -97,6 +97,45 @@ def spmv(indptr, indices, data, x, omp: bool = False):
     return y
 
 
+def random_csr(m, n, nnz_total, seed, r0=0, r1=None, lo=0.0, hi=1.0):
+    """Host twin of the device generator behind legate_sparse.random (b2s_gallery.cu): rows
+    [r0, r1) as (indptr_local, indices int64, data f64).  Arrays are first-touched by the OpenMP
+    threads that fill them (what bench.py's CPU arm wants)."""
+    r1 = m if r1 is None else r1
+    q, rem = divmod(int(nnz_total), int(m))
+    # block nnz from the closed form (same as b2s_random_csr_block_nnz)
+    mask = (1 << 64) - 1
+
+    def mix(t):
+        t = ((t ^ (t >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        t = ((t ^ (t >> 27)) * 0x94D049BB133111EB) & mask
+        return t ^ (t >> 31)
+
+    shift = mix(int(seed) & mask) % int(m)
+
+    def extras(a):
+        return (a // m) * rem + min(a % m, rem)
+
+    def start(i):
+        return i * q + extras(i + shift) - extras(shift)
+
+    nloc = r1 - r0
+    nnz_loc = start(r1) - start(r0)
+    indptr = np.empty(nloc + 1, dtype=np.int64)
+    crd = np.empty(nnz_loc, dtype=np.int64)
+    vals = np.empty(nnz_loc, dtype=np.float64)
+    _lib().ref_random_csr_f64(ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(nnz_total),
+                              ctypes.c_uint64(int(seed) & mask), ctypes.c_int64(r0), ctypes.c_int64(r1),
+                              ctypes.c_double(lo), ctypes.c_double(hi), _p(indptr), _p(crd), _p(vals))
+    return indptr, crd, vals
+
+
+def fill_uniform(n, seed):
+    x = np.empty(int(n), dtype=np.float64)
+    _lib().ref_fill_uniform_f64(ctypes.c_int64(n), ctypes.c_uint64(int(seed) & ((1 << 64) - 1)), _p(x))
+    return x
+
+
 def spgemm(a_ptr, a_idx, a_val, b_ptr, b_idx, b_val, ncolsB):
     """C = A B, reference two-pass CPU path: NNZ task (spgemm_csr_csr_csr.cc:62-87), cumsum
     (base.py:67-87), numeric task (:134-158).  Output columns in first-touch order."""

@@ -209,3 +209,59 @@ void ref_expand_rows(int64_t nrows, const int64_t* indptr, int64_t* rows_out)
   for (int64_t i = 0; i < nrows; i++)
     for (int64_t j = indptr[i]; j < indptr[i + 1]; j++) rows_out[j] = i;
 }
+
+/* ---- legate_sparse.random: host twin of the device generator (legate-sparse_b200/csrc/
+ *      b2s_gallery.cu, random_fill_kernel).  No upstream counterpart (the reference's tests densify
+ *      cupynumeric random arrays, tests/integration/utils/sample.py:21-45); this restatement is the
+ *      checker of the device generator and the generator of the CPU arm's matrix in bench.py
+ *      (parallel first touch: every thread initialises the rows it will later multiply). --------- */
+static uint64_t ref_mix64(uint64_t t)
+{
+  t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull;
+  t = (t ^ (t >> 27)) * 0x94D049BB133111EBull;
+  return t ^ (t >> 31);
+}
+static int64_t ref_extras_before(int64_t a, int64_t m, int64_t rem)
+{
+  return (a / m) * rem + ((a % m) < rem ? (a % m) : rem);
+}
+static int64_t ref_row_start(int64_t i, int64_t m, int64_t q, int64_t rem, int64_t shift)
+{
+  return i * q + ref_extras_before(i + shift, m, rem) - ref_extras_before(shift, m, rem);
+}
+
+#include <math.h>
+/* rows [r0, r1) of the m x n matrix with nnz_total entries; indptr_local has r1-r0+1 entries
+ * (0-based), crd/vals hold indptr_local[r1-r0] entries; values uniform in [lo, hi). */
+void ref_random_csr_f64(int64_t m, int64_t n, int64_t nnz_total, uint64_t seed, int64_t r0, int64_t r1,
+                        double lo, double hi, int64_t* indptr_local, int64_t* crd, double* vals)
+{
+  const int64_t q = nnz_total / m, rem = nnz_total % m;
+  const int64_t shift = (int64_t)(ref_mix64(seed) % (uint64_t)m);
+  const int64_t base0 = ref_row_start(r0, m, q, rem, shift);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = r0; i < r1; i++) {
+    const int64_t k    = q + (((i + shift) % m) < rem ? 1 : 0);
+    const int64_t base = ref_row_start(i, m, q, rem, shift) - base0;
+    indptr_local[i - r0] = base;
+    if (i == r1 - 1) indptr_local[r1 - r0] = base + k;
+    const uint64_t rowkey = ref_mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1));
+    for (int64_t j = 0; j < k; j++) {
+      const uint64_t s0 = (uint64_t)(((unsigned __int128)(uint64_t)j * (uint64_t)n) / (uint64_t)k);
+      const uint64_t s1 = (uint64_t)(((unsigned __int128)(uint64_t)(j + 1) * (uint64_t)n) / (uint64_t)k);
+      const uint64_t h  = ref_mix64(rowkey + (uint64_t)j);
+      crd[base + j]     = (int64_t)(s0 + h % (s1 - s0));
+      const uint64_t h2 = ref_mix64(h ^ 0x632BE59BD9B4E019ull);
+      vals[base + j]    = fma(hi - lo, (double)(h2 >> 11) * (1.0 / 9007199254740992.0), lo);
+    }
+  }
+  if (r1 == r0) indptr_local[0] = 0;
+}
+
+/* y and x for the CPU arm, first-touched in parallel like the matrix */
+void ref_fill_uniform_f64(int64_t n, uint64_t seed, double* x)
+{
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; i++)
+    x[i] = (double)(ref_mix64(seed + (uint64_t)i) >> 11) * (1.0 / 9007199254740992.0);
+}

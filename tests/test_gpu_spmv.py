@@ -239,3 +239,22 @@ def test_diagonal_and_transpose_device():
     Ad = sparse.csr_array((torch.from_numpy(S.data).cuda(), torch.from_numpy(S.indices.astype(np.int64)).cuda(),
                            torch.from_numpy(S.indptr.astype(np.int64)).cuda()), shape=S.shape)
     assert np.array_equal(Ad.T.todense(), np.asarray(S.todense()).T)
+def test_longrows_pass_on_skewed_rows(monkeypatch):
+    """power-law row lengths: rows much longer than the tile average are summed by a full warp in a
+    second pass of the products consumer (selected from the plan's max row; forced here as well)."""
+    import scipy.sparse as sp
+    import legate_sparse as sparse
+    from tests import gen
+
+    d, c, p = gen.powerlaw_csr(60000, 60000, max_row=5000, seed=11)
+    S = sp.csr_array((d, c, p), shape=(60000, 60000))
+    x = np.random.default_rng(4).standard_normal(60000)
+    want = S @ x
+    for force in (None, "1", "0"):
+        if force is None:
+            monkeypatch.delenv("B2S_SPMV_LONGROWS", raising=False)
+        else:
+            monkeypatch.setenv("B2S_SPMV_LONGROWS", force)
+        A = sparse.csr_array(S)
+        y = A @ x
+        assert np.allclose(y, want, rtol=1e-11, atol=1e-11), force
