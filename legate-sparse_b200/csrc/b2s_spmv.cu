@@ -22,6 +22,7 @@ namespace b2s {
 
 constexpr int kTileThreads = 256;
 constexpr int kWinCap      = 1024;  // x-window capacity in elements (== kPipeWinCap)
+constexpr int kNearSpan    = 12288; // elements of x a tile may span and still live in L1 (96 KB of fp64)
 
 struct PlanHeader {  // host-side plan object
   b2s_itype it;
@@ -36,6 +37,8 @@ struct PlanHeader {  // host-side plan object
   void*    dotp;       // [ntiles] * 16 bytes (per-tile partials of the fused dot)
   int64_t  empty_rows; // number of rows without non-zeros
   int64_t  max_row;    // longest row (nnz) — selects the long-row pass of the products consumer
+  int64_t  near_tiles; // tiles whose [min col, max col] image is <= kNearSpan elements: their x gathers
+                       // re-hit L1 (products consumer then allocates the gathers in L1)
   int64_t* counters;   // [4]
 };
 
@@ -102,6 +105,7 @@ __global__ void plan_tile_window_kernel(int64_t nnz, int64_t ntiles, int64_t til
     tile_win[2 * t]     = fits ? base : 0;
     tile_win[2 * t + 1] = fits ? cnt : 0;
     if (fits) atomicAdd((unsigned long long*)&counters[0], 1ull);
+    if (mn >= 0 && mx - mn < kNearSpan) atomicAdd((unsigned long long*)&counters[4], 1ull);
     int64_t r0 = tile_row[t];
     if (indptr[r0] < S) atomicAdd((unsigned long long*)&counters[1], 1ull);
   }
@@ -358,10 +362,6 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-// Products-consumer configuration (tools/spmv_sweep varies it through the environment):
-//   B2S_SPMV_GROUPS   1 | 2      consumer groups per CTA (default 2: ping-pong)
-static int pipe_groups_default() { int g = env_int("B2S_SPMV_GROUPS", 2); return g == 1 ? 1 : 2; }
-
 template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG, bool LONGROWS = false>
 static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
@@ -375,12 +375,16 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   int nb = blocks_per_sm[dev].load(std::memory_order_acquire);
   if (nb <= 0) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // Every x gather in flight holds an L1 line, so the gather-bound products kernel wants L1, not
-    // shared memory: two CTAs with the 132 KB shared-memory configuration (L1 = 124 KB) beat the
-    // three CTAs the occupancy API offers (196 KB, L1 = 60 KB): 2.30 vs 2.375 ms on the
-    // column-blocked C2 matrix; a 228 KB carve-out costs 65 % (tools/gpu_occ.sh).
-    // B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
-    int carve = !WINDOW ? 55 : -1, cap = !WINDOW ? 2 : 0;
+    // Resident CTAs / shared-memory carve-out of the products consumer, measured on C2 (random,
+    // column-blocked), the 4096^2 Laplacian and the power-law matrix (profiles/r2_occ_sweep.txt):
+    //   4-stage ring, 3 CTAs/SM (173 KB of shared memory, carve-out 80 %): 2.20 / 0.275 / 0.568 ms
+    //   4-stage ring, 2 CTAs/SM (carve-out 55 %, L1 = 124 KB)            : 2.32 / 0.357 / 0.505 ms
+    //   2-stage ring, 3 CTAs/SM (carve-out 44 %)                         : 2.60 / 0.364 / 0.488 ms
+    // Round 1 preferred 2 CTAs + a large L1 because its gathers allocated L1 lines; with
+    // L1::no_allocate gathers the third CTA wins.  The long-row (power-law) instances run the
+    // shallow ring.  B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
+    int carve = -1, cap = 0;
+    if (!WINDOW) { cap = 3; carve = LONGROWS ? 50 : 80; }
     carve = env_int("B2S_SPMV_CARVEOUT", carve);
     cap = env_int("B2S_SPMV_CTAS", cap);
     if (carve >= 0) B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -392,10 +396,11 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   int64_t grid = (int64_t)nb * num_sms();
   if (grid > P->ntiles) grid = P->ntiles;
   *npartials = grid;
+  const int l1_alloc = env_int("B2S_SPMV_L1_ALLOC", P->near_tiles * 2 >= P->ntiles ? 1 : 0) != 0;
   kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals,
                                                    x, y, P->tile_row, P->tile_win,
                                                    reinterpret_cast<V*>(P->head), dot_partials, w, peers,
-                                                   accumulate);
+                                                   (accumulate ? 1 : 0) | (l1_alloc ? 2 : 0));
   B2S_CHECK_LAUNCH();
   return B2S_OK;
 }
@@ -407,7 +412,7 @@ static int launch_pipe_tile(const PlanHeader* P, const int64_t* indptr, const I*
   bool window = (P->window_tiles * 2 >= P->ntiles) && ((uintptr_t)x % 16 == 0) &&
                 getenv("B2S_SPMV_NO_WINDOW") == nullptr;
   // window matrices (banded / stencil): row-walk consumer, 2-stage ring; others: products consumer
-  // with two ping-pong consumer groups on a 4-stage ring of 1024-nnz tiles (or one group / 2 stages).
+  // with two ping-pong consumer groups (1024-nnz tiles: 4-stage ring, 2048-nnz tiles: 2 stages).
   // Peer stores are compiled in only for the broadcast launches.
   const bool bcast = peers.n != 0;
 #define B2S_PIPE(S, W, B, G) launch_pipe_inst<V, I, TILE, S, W, DOT, B, G>(P, indptr, cols, vals, x, y, dot_partials, w, npartials, peers, accumulate, st)
@@ -418,14 +423,11 @@ static int launch_pipe_tile(const PlanHeader* P, const int64_t* indptr, const I*
   longrows = env_int("B2S_SPMV_LONGROWS", longrows ? 1 : 0) != 0;
   if constexpr (!DOT && TILE == 1024) {
     if (longrows && !bcast)
-      return launch_pipe_inst<V, I, TILE, 4, false, false, false, 2, true>(P, indptr, cols, vals, x, y, dot_partials, w,
+      return launch_pipe_inst<V, I, TILE, 2, false, false, false, 2, true>(P, indptr, cols, vals, x, y, dot_partials, w,
                                                                           npartials, peers, accumulate, st);
   }
-  if (pipe_groups_default() == 2) {
-    if constexpr (TILE == 1024) return bcast ? B2S_PIPE(4, false, true, 2) : B2S_PIPE(4, false, false, 2);
-    else                        return bcast ? B2S_PIPE(2, false, true, 2) : B2S_PIPE(2, false, false, 2);
-  }
-  return bcast ? B2S_PIPE(2, false, true, 1) : B2S_PIPE(2, false, false, 1);
+  if constexpr (TILE == 1024) return bcast ? B2S_PIPE(4, false, true, 2) : B2S_PIPE(4, false, false, 2);
+  else                        return bcast ? B2S_PIPE(2, false, true, 2) : B2S_PIPE(2, false, false, 2);
 #undef B2S_PIPE
 }
 
@@ -638,7 +640,7 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
     P->tile_win = reinterpret_cast<int64_t*>(base);               base += nt * 16;
     P->head = reinterpret_cast<void*>(base);                      base += nt * 16;
     P->dotp = reinterpret_cast<void*>(base);                      base += nt * 16;
-    P->empty_rows = 0; P->max_row = 0;
+    P->empty_rows = 0; P->max_row = 0; P->near_tiles = 0;
     if (nt == 0) break;
     cudaError_t e = cudaMemsetAsync(P->counters, 0, 64, st);
     if (e != cudaSuccess) { delete P; set_error("memset failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
@@ -659,15 +661,16 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
       plan_count_empty_kernel<<<(unsigned)blocks, 256, 0, st>>>(nrows, indptr, P->counters);
       g_launch_count.fetch_add(1);
     }
-    int64_t h[4] = {0, 0, 0, 0};
+    int64_t h[5] = {0, 0, 0, 0, 0};
     e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 40, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { delete P; set_error("plan build failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
     P->window_tiles = h[0];
     P->head_tiles = h[1];
     P->empty_rows = h[2];
     P->max_row = h[3];
+    P->near_tiles = h[4];
     if (forced || P->window_tiles * 2 >= P->ntiles) break;   // keep this tiling
   }
   *out_plan = P;

@@ -93,7 +93,10 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const V* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
                  const int64_t* __restrict__ tile_row, const int64_t* __restrict__ tile_win,
                  V* __restrict__ head, V* __restrict__ dot_partials, const V* __restrict__ w,
-                 const PeerOut<V> peers, const int accumulate) {
+                 const PeerOut<V> peers, const int flags) {
+  const int accumulate = flags & 1;        // y += A x (later column blocks)
+  const bool l1_alloc  = (flags & 2) != 0; // products consumer: gathers allocate in L1 (matrices whose
+                                           // tiles re-touch a small x range, e.g. wide-band stencils)
   using L = PipeLayout<V, I, TILE>;
   constexpr int T = L::T;
   constexpr bool ROWWALK = WINDOW;
@@ -225,7 +228,10 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         // Gathers are issued in batches of BCH chunks = 4 gathers per thread.  Measured on the
         // column-blocked C2 matrix (profiles/r2_pipe_sweep.txt): all 8 of a thread at once 2.40 ms,
         // 4 at a time 2.29 ms, 2 at a time 2.41 ms; with L1::no_allocate on the gathers (their L1
-        // hit rate is 0.5 %, so a line per outstanding request buys nothing) 2.23 ms.
+        // hit rate is 0.5 %, so a line per outstanding request buys nothing) 2.23 ms.  Matrices
+        // whose tiles keep re-touching a small range of x (the 4096^2 Laplacian: 8 K elements per
+        // tile) want the opposite: with no_allocate their SpMV went from 0.276 to 0.349 ms, so the
+        // plan's "near tiles" statistic selects the allocating load for them (flag bit 1).
         constexpr int BCH = (4 / C) > 0 ? ((4 / C) < NCH ? (4 / C) : NCH) : 1;
         static_assert(NCH % BCH == 0, "chunks per thread must be a multiple of the gather batch");
 #pragma unroll
@@ -239,10 +245,17 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
             pc[u] = *reinterpret_cast<const IC*>(scols + e);   // LDS.64 / LDS.128, conflict-free
             pv[u] = *reinterpret_cast<const VC*>(svals + e);   // LDS.128, conflict-free
           }
+          if (l1_alloc) {
 #pragma unroll
-          for (int u = 0; u < BCH; ++u)
+            for (int u = 0; u < BCH; ++u)
 #pragma unroll
-            for (int j = 0; j < C; ++j) xv[u][j] = ld_gather_na<V>(x + (int64_t)pc[u].c[j], pol_keep);
+              for (int j = 0; j < C; ++j) xv[u][j] = ld_gather<V>(x + (int64_t)pc[u].c[j], pol_keep);
+          } else {
+#pragma unroll
+            for (int u = 0; u < BCH; ++u)
+#pragma unroll
+              for (int j = 0; j < C; ++j) xv[u][j] = ld_gather_na<V>(x + (int64_t)pc[u].c[j], pol_keep);
+          }
 #pragma unroll
           for (int u = 0; u < BCH; ++u) {
 #pragma unroll
@@ -320,7 +333,10 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           if (lane == 0) finish_row(r, lo_g, sum, accumulate ? y[r] : zero_of<V>());
         }
       }
-      fence_proxy_async_smem();
+      // the product stores above are generic-proxy writes to memory the TMA refills later: the
+      // cross-proxy fence is issued ONCE, by the producer, after it has acquired this arrival
+      // (fence.proxy.async = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: 4 % of the kernel when all 256
+      // consumer threads executed it per tile)
       mbar_arrive(&empty_bar[s]);
     }
     if (DOT) {

@@ -586,6 +586,92 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
 
 
 # ======================================================================= GMRES
+def _gmres_sharded(A, b_dev, x, dtype, atol, restart, maxiter, callback, callback_type, b_norm, numpy_mode):
+    """Restarted GMRES on ROW-SHARDED vectors (identity preconditioner, several ranks): every rank
+    keeps rows [r0, r1) of the Krylov basis, of u and of x — the partition the reference gets from
+    Legate for ``V[:, :j+1].conj().T @ u`` (linalg.py:628-631).  Per Arnoldi step: one SpMV on the
+    local rows (needs the replicated v_j: one all-gather of n values), local CGS kernels, and two
+    small all-reduces (the j+1 projections, the norm).  Same arithmetic as the replicated path except
+    for the order of the cross-rank sums."""
+    from . import _device as D
+    from .csr import _spmv_block
+
+    G = dist.world_size()
+    n = A.shape[0]
+    blk = A._block()
+    bounds = A.row_bounds()
+    r0, r1 = blk.r0, blk.r1
+    nl = r1 - r0
+    tdt = D.torch_dtype(dtype)
+    rdt = D.torch_dtype(D.real_dtype(dtype))
+    dev = b_dev.device
+    ldv = (max(nl, 1) + 31) // 32 * 32
+    V = torch.empty((restart, ldv), dtype=tdt, device=dev)        # local rows of the basis vectors
+    H = torch.zeros((restart + 1, restart), dtype=tdt, device=dev)
+    hcol = torch.empty(restart, dtype=tdt, device=dev)
+    hn = torch.empty(1, dtype=rdt, device=dev)
+    e = np.zeros((restart + 1,), dtype=dtype)
+    z_full = torch.empty(n, dtype=tdt, device=dev)                # replicated operand of the SpMV
+    u = torch.empty(nl, dtype=tdt, device=dev)
+    x_loc = x[r0:r1].clone()
+    b_loc = b_dev[r0:r1]
+
+    def gather(v_loc):
+        z_full[r0:r1].copy_(v_loc)
+        dist.allgather_into(z_full, bounds)
+        return z_full
+
+    def norm_all(sq_holder):
+        """global 2-norm from the local one in sq_holder (device real scalar), in place"""
+        sq_holder.mul_(sq_holder)
+        dist.allreduce_sum_(sq_holder)
+        sq_holder.sqrt_()
+
+    iters = 0
+    while True:
+        _spmv_block(A, blk, gather(x_loc), u)                      # u = (A x)_loc
+        r = b_loc - u
+        D.nrm2(r, out=hn)
+        norm_all(hn)
+        r_norm = float(hn.item())
+        if callback_type == "x":
+            xf = dist.allgather_rows(x_loc, bounds)
+            callback(D.to_host(xf) if numpy_mode else xf)
+        elif callback_type == "pr_norm" and iters > 0:
+            callback(r_norm / b_norm)
+        if r_norm <= atol or iters >= maxiter:
+            break
+        if nl > 0:
+            D.vscale_inv(r, hn, V[0, :nl])
+        e[:] = 0
+        e[0] = r_norm
+        for j in range(restart):
+            _spmv_block(A, blk, gather(V[j, :nl]), u)              # u = (A v_j)_loc
+            if nl > 0:
+                D.cgs_project(V, ldv, nl, j + 1, u, hcol)          # local part of V_j^H u
+            else:
+                hcol.zero_()
+            dist.allreduce_sum_(hcol[: j + 1])
+            if nl > 0:
+                D.cgs_update(V, ldv, nl, j + 1, hcol, u, negate=True, nrm_out=hn)   # u -= V_j h ; hn = ||u_loc||
+            else:
+                hn.zero_()
+            norm_all(hn)
+            H[: j + 1, j] = hcol[: j + 1]
+            H[j + 1, j] = hn[0]
+            if j + 1 < restart and nl > 0:
+                D.vscale_inv(u, hn, V[j + 1, :nl])
+        y = np.linalg.lstsq(D.to_host(H), e, rcond=None)[0]       # identical on every rank
+        y_dev = D.to_device(np.ascontiguousarray(y), dtype=dtype)
+        if nl > 0:
+            D.cgs_update(V, ldv, nl, restart, y_dev, x_loc, negate=False)   # x += V y
+        iters += restart
+    info = 0
+    if iters == maxiter and not (r_norm <= atol):
+        info = iters
+    return dist.allgather_rows(x_loc, bounds), info
+
+
 def gmres(
     A,
     b,
@@ -641,6 +727,12 @@ def gmres(
         raise ValueError("Unknown callback_type: {}".format(callback_type))
     if callback is None:
         callback_type = None
+
+    if dist.world_size() > 1 and Ad.csr is not None and Md.is_identity and Ad.csr.dtype == dtype and \
+            os.environ.get("LEGATE_SPARSE_GMRES_REPLICATED", "0") in ("0", ""):
+        mx, info = _gmres_sharded(Ad.csr, b_dev, x, dtype, atol, restart, maxiter, callback, callback_type, b_norm,
+                                  numpy_mode)
+        return _vec_out(mx, b), info
 
     dev = b_dev.device
     # Krylov basis, basis-vector-major (row c = v_c): every kernel streams unit-stride rows.

@@ -8,7 +8,7 @@ only kernel-selection switches survive here — the Legate settings machinery is
   B2S_SPMV_VARIANT=auto|rowvec|tile|pipe   (auto = pipe when a plan exists and the arrays are 16-byte
                               aligned, else tile, else rowvec)
   B2S_SPMV_TILE_NNZ=1024|2048|4096   (read by the native library)
-  B2S_SPMV_GROUPS=1|2                (read by the native library) consumer groups of the pipe kernel
+  B2S_SPMV_LONGROWS=0|1              (read by the native library) force the long-row pass off / on
   B2S_SPMV_NO_WINDOW=1               (read by the native library) disable TMA x-window staging
 """
 import os

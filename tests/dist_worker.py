@@ -109,6 +109,44 @@ def main():
     assert np.array_equal(C2.indptr, E2.indptr) and relerr(C2.data, E2.data) < 1e-12
     # distributed diagonal
     assert np.allclose(Ad.diagonal(), P.diagonal())
+    # --- host vectors: x uploaded in 1/G slices + NVLink all-gather; dot_local returns this rank's rows
+    yh = A.dot_local(x)
+    assert relerr(yh, (S @ x)[blk.r0 : blk.r1]) < 1e-12
+    out_blk = torch.empty(blk.nrows, dtype=torch.float64).pin_memory()
+    A.dot_local(torch.from_numpy(x).pin_memory(), out=out_blk)
+    assert relerr(out_blk.numpy(), (S @ x)[blk.r0 : blk.r1]) < 1e-12
+    # several calls in a row: the replicated result buffers alternate (no opening barrier)
+    for s_ in (1.0, 2.0, 3.0, 4.0):
+        assert relerr(A @ (s_ * x), s_ * (S @ x)) < 1e-12
+    # --- in-kernel all-reduce through the peer-mapped boards: deterministic, same on every rank
+    board = dist.scalar_board()
+    if board is not None:
+        for it in range(6):
+            t = torch.tensor([float(rank + 1) * 0.1 + it], dtype=torch.float64, device="cuda")
+            board.allreduce(t, it % 3)
+            want = sum((g + 1) * 0.1 + it for g in range(G))     # summed in rank order, like the kernel
+            acc = 0.0
+            for g in range(G):
+                acc += float((g + 1) * 0.1 + it)
+            assert t.item() == acc, (t.item(), acc, want)
+        cur, prev = torch.tensor([5.0], device="cuda", dtype=torch.float64), torch.zeros(1, device="cuda", dtype=torch.float64)
+        t = torch.tensor([1.0], dtype=torch.float64, device="cuda")
+        board.allreduce(t, 2, cur_out=cur, prev_out=prev)
+        assert prev.item() == 5.0 and cur.item() == float(G) and t.item() == float(G)
+        board.check()
+    # --- GMRES on row-sharded vectors (local CGS kernels + small all-reduces) vs the oracle / scipy residual
+    ng = 3000
+    Wg = sp.random(ng, ng, density=0.002, format="csr", random_state=21) + sp.eye(ng, format="csr") * 4.0
+    Wg = Wg.tocsr()
+    bg = rng.standard_normal(ng)
+    xg, info = linalg.gmres(sparse.csr_array(Wg), bg, rtol=1e-10, restart=20, maxiter=400)
+    assert info == 0 and relerr(Wg @ xg, bg) < 1e-9
+    xo_g, _ = oracle.gmres(lambda v: Wg @ v, bg, rtol=1e-10, restart=20, maxiter=400)
+    assert relerr(xg, xo_g) < 1e-8
+    os.environ["LEGATE_SPARSE_GMRES_REPLICATED"] = "1"
+    xr, _ = linalg.gmres(sparse.csr_array(Wg), bg, rtol=1e-10, restart=20, maxiter=400)
+    os.environ.pop("LEGATE_SPARSE_GMRES_REPLICATED")
+    assert relerr(xg, xr) < 1e-9
     torch.cuda.synchronize()
     print(f"rank {rank}/{G} OK", flush=True)
     dist.shutdown()

@@ -71,13 +71,13 @@ def test_spmv_variants_types(monkeypatch, variant, index64, dtype):
     assert relerr(y, S @ x) < tol
 
 
-@pytest.mark.parametrize("groups,tile", [("1", "1024"), ("1", "2048"), ("2", "1024"), ("2", "2048")])
+@pytest.mark.parametrize("longrows,tile", [("0", "1024"), ("1", "1024"), ("0", "2048")])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
-def test_spmv_pipe_groups_irregular_rows(monkeypatch, dtype, groups, tile):
-    """products consumer of the TMA pipe kernel, one group or two ping-pong groups, both tile
-    sizes: irregular rows, empty rows, rows longer than a tile"""
+def test_spmv_pipe_products_irregular_rows(monkeypatch, dtype, longrows, tile):
+    """products consumer of the TMA pipe kernel (two ping-pong groups), both tile sizes, with and
+    without the long-row pass: irregular rows, empty rows, rows longer than a tile"""
     monkeypatch.setenv("B2S_SPMV_VARIANT", "pipe")
-    monkeypatch.setenv("B2S_SPMV_GROUPS", groups)
+    monkeypatch.setenv("B2S_SPMV_LONGROWS", longrows)
     monkeypatch.setenv("B2S_SPMV_TILE_NNZ", tile)
     monkeypatch.setenv("B2S_SPMV_NO_WINDOW", "1")
     rng = np.random.default_rng(12)

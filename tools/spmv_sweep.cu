@@ -2,7 +2,7 @@
 // Links against libb200sparse.so through the public C ABI; also measures two ceilings:
 //   stream : read (col,val) arrays only           → HBM streaming ceiling for this access shape
 //   gather : read col + gather x[col] (no vals)   → L2/L1tex gather ceiling
-// Usage: spmv_sweep [rows=10000000] [k=50] [iters=20] [mode=random|banded]
+// Usage: spmv_sweep [rows=10000000] [k=50] [iters=20] [mode=random|banded|poisson]   (poisson: rows = grid side N)
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -54,6 +54,25 @@ __global__ void banded_counts(int64_t n, int k, int64_t* cnt) {
   int half = k / 2;
   int64_t lo = r - half < 0 ? 0 : r - half, hi = r + half > n - 1 ? n - 1 : r + half;
   cnt[r] = hi - lo + 1;
+}
+
+// 5-point Laplacian on an N x N grid (BASELINE config 3): row i has columns i-N, i-1, i, i+1, i+N inside the grid
+__global__ void poisson_counts(int64_t N, int64_t* cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * N) return;
+  int64_t gi = i / N, gj = i % N;
+  cnt[i] = 1 + (gi > 0) + (gi < N - 1) + (gj > 0) + (gj < N - 1);
+}
+template <typename I>
+__global__ void gen_poisson(int64_t N, I* cols, double* vals, const int64_t* indptr) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * N) return;
+  int64_t gi = i / N, gj = i % N, p = indptr[i];
+  if (gi > 0)     { cols[p] = (I)(i - N); vals[p++] = -1.0; }
+  if (gj > 0)     { cols[p] = (I)(i - 1); vals[p++] = -1.0; }
+  cols[p] = (I)i; vals[p++] = 4.0;
+  if (gj < N - 1) { cols[p] = (I)(i + 1); vals[p++] = -1.0; }
+  if (gi < N - 1) { cols[p] = (I)(i + N); vals[p++] = -1.0; }
 }
 
 __global__ void fill_x(int64_t n, double* x) {
@@ -164,6 +183,8 @@ double run_case(const char* name, b2s_itype it, int64_t n, int64_t m, int64_t nn
 
 int main(int argc, char** argv) {
   int64_t n = argc > 1 ? atoll(argv[1]) : 10000000;
+  const int64_t gridN = n;   // mode=poisson: argv[1] is the grid side N, the matrix has N*N rows
+  if (argc > 4 && std::string(argv[4]) == "poisson") n = gridN * gridN;
   int k = argc > 2 ? atoi(argv[2]) : 50;
   int iters = argc > 3 ? atoi(argv[3]) : 20;
   std::string mode = argc > 4 ? argv[4] : "random";
@@ -188,6 +209,14 @@ int main(int argc, char** argv) {
     for (int64_t i = 0; i < n; ++i) h[i + 1] = h[i] + hc[i];
     CK(cudaMemcpy(indptr, h.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
     nnz = h[n]; cudaFree(cnt);
+  } else if (mode == "poisson") {
+    int64_t* cnt; CK(cudaMalloc(&cnt, n * 8));
+    poisson_counts<<<(unsigned)((n + 255) / 256), 256>>>(gridN, cnt);
+    std::vector<int64_t> h(n + 1, 0), hc(n);
+    CK(cudaMemcpy(hc.data(), cnt, n * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) h[i + 1] = h[i] + hc[i];
+    CK(cudaMemcpy(indptr, h.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+    nnz = h[n]; cudaFree(cnt);
   } else nnz = n * k;
   int32_t* c32; int64_t* c64; double *vals, *x, *y, *sink;
   CK(cudaMalloc(&c32, nnz * 4)); CK(cudaMalloc(&c64, nnz * 8)); CK(cudaMalloc(&vals, nnz * 8));
@@ -195,6 +224,9 @@ int main(int argc, char** argv) {
   if (mode == "banded") {
     gen_banded<int32_t><<<(unsigned)((n + 255) / 256), 256>>>(n, k, c32, vals, indptr);
     gen_banded<int64_t><<<(unsigned)((n + 255) / 256), 256>>>(n, k, c64, vals, indptr);
+  } else if (mode == "poisson") {
+    gen_poisson<int32_t><<<(unsigned)((n + 255) / 256), 256>>>(gridN, c32, vals, indptr);
+    gen_poisson<int64_t><<<(unsigned)((n + 255) / 256), 256>>>(gridN, c64, vals, indptr);
   } else {
     gen_random<int32_t><<<148 * 16, 256>>>(n, m, k, c32, vals, indptr);
     gen_random<int64_t><<<148 * 16, 256>>>(n, m, k, c64, vals, indptr);
@@ -202,10 +234,9 @@ int main(int argc, char** argv) {
   fill_x<<<(unsigned)((m + 255) / 256), 256>>>(m, x);
   CK(cudaDeviceSynchronize());
 
-  // single-config mode (for ncu): spmv_sweep n k iters mode single <variant 1|2|3> <tile> <groups> [i64]
+  // single-config mode (for ncu): spmv_sweep n k iters mode single <variant 1|2|3> <tile> <unused> [i64]
   if (argc > 8 && std::string(argv[5]) == "single") {
     int variant = atoi(argv[6]), tile = atoi(argv[7]);
-    setenv("B2S_SPMV_GROUPS", argv[8], 1);
     bool i64 = argc > 9 && std::string(argv[9]) == "i64";
     if (i64) run_case<int64_t>("single", B2S_I64, n, m, nnz, indptr, c64, vals, x, y, variant, tile, iters, false);
     else     run_case<int32_t>("single", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, variant, tile, iters, false);
@@ -231,18 +262,11 @@ int main(int argc, char** argv) {
     return 0;
   }
   int tiles[2] = {1024, 2048};
-  const char* grp[2] = {"1", "2"};
-  for (int gi = 0; gi < 2; ++gi)
-    for (int ti = 0; ti < 2; ++ti) {
-      setenv("B2S_SPMV_GROUPS", grp[gi], 1);
-      char nm[64]; snprintf(nm, sizeof nm, "pipe groups=%s", grp[gi]);
-      run_case<int32_t>(nm, B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_PIPE, tiles[ti], iters, false);
-      if (mode == "banded") {
-        snprintf(nm, sizeof nm, "pipe groups=%s (no x window)", grp[gi]);
-        run_case<int32_t>(nm, B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_PIPE, tiles[ti], iters, true);
-      }
-    }
-  unsetenv("B2S_SPMV_GROUPS");
+  for (int ti = 0; ti < 2; ++ti) {
+    run_case<int32_t>("pipe", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_PIPE, tiles[ti], iters, false);
+    if (mode == "banded")
+      run_case<int32_t>("pipe (no x window)", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_PIPE, tiles[ti], iters, true);
+  }
   run_case<int64_t>("pipe", B2S_I64, n, m, nnz, indptr, c64, vals, x, y, B2S_SPMV_PIPE, 2048, iters, false);
   run_case<int32_t>("tile", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_TILE, 1024, iters, true);
   run_case<int32_t>("rowvec", B2S_I32, n, m, nnz, indptr, c32, vals, x, y, B2S_SPMV_ROWVEC, 0, iters, false);
