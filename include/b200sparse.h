@@ -155,7 +155,8 @@ int b2s_spmv_colblock(const b2s_colblock* cb, const void* x, void* y, const void
                       void* const* y_peers, int npeers, b2s_stream_t stream);
 /* Block `block` of that sequence only (call for 0..nblocks-1 in order).  Block b reads only
  * x[b*block_cols, (b+1)*block_cols), so a host caller can overlap the H2D copy of the next slice
- * of x with this launch. */
+ * of x with this launch.  `block | (1 << 30)` forces the accumulating form y += A_b x (for a caller
+ * that computed the earlier blocks of the same rows with another operand: 2-D row x column blocks). */
 int b2s_spmv_colblock_part(const b2s_colblock* cb, int block, const void* x, void* y,
                            b2s_stream_t stream);
 

@@ -344,10 +344,14 @@ extern "C" int b2s_spmv_colblock(const b2s_colblock* cb, const void* x, void* y,
 
 // One block of the sequence above (block `b` only): lets the caller overlap the host->device copy
 // of x slice b+1 with the launch of block b (the slice [b*block_cols, (b+1)*block_cols) of x is
-// all that block b reads).  Call for b = 0..nblocks-1 in order.
+// all that block b reads).  Call for b = 0..nblocks-1 in order.  `block | (1 << 30)` forces the
+// accumulating form (y += A_b x) for callers that computed the earlier blocks with another operand
+// of the same rows (the 2-D host pipeline).
 extern "C" int b2s_spmv_colblock_part(const b2s_colblock* cb, int block, const void* x, void* y,
                                       b2s_stream_t stream) {
   B2S_REQUIRE(cb != nullptr, "colblock is null");
+  const bool force_acc = (block & (1 << 30)) != 0;   // bit 30: y += A_b x whatever the block's position
+  block &= ~(1 << 30);
   B2S_REQUIRE(block >= 0 && block < cb->nblocks, "block out of range");
   B2S_REQUIRE(x != nullptr && y != nullptr, "null vector");
   if (cb->blk_nnz[block] == 0) return B2S_OK;
@@ -355,5 +359,5 @@ extern "C" int b2s_spmv_colblock_part(const b2s_colblock* cb, int block, const v
   while (cb->blk_nnz[first] == 0) ++first;
   return spmv_entry(cb->vt, cb->it, cb->nrows, cb->ncols, cb->blk_nnz[block], cb->indptr[block],
                     cb->cols[block], cb->vals[block], x, y, cb->plan[block], B2S_SPMV_PIPE, nullptr,
-                    nullptr, nullptr, nullptr, 0, block != first, stream);
+                    nullptr, nullptr, nullptr, 0, (block != first || force_acc) ? 1 : 0, stream);
 }

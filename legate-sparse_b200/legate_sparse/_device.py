@@ -258,6 +258,11 @@ class ColBlock:
         """one column block of the sequence (block b only reads slice b of x)"""
         N.check(self._lib.b2s_spmv_colblock_part(self.handle, b, ptr(x), ptr(y), stream_ptr()), "spmv_colblock_part")
 
+    def spmv_part_accumulate(self, b, x, y):
+        """y += A_b x for block b, whatever its position (y already holds the earlier blocks)"""
+        N.check(self._lib.b2s_spmv_colblock_part(self.handle, b | (1 << 30), ptr(x), ptr(y), stream_ptr()),
+                "spmv_colblock_part")
+
     def __del__(self):
         try:
             if self.handle:
@@ -277,8 +282,9 @@ class HostPipe:
     next chunks are still being computed.  Built once per matrix (holds a second column-blocked
     copy of the values, like ColBlock)."""
 
-    def __init__(self, vt, it, nrows, ncols, indptr, indices, data, nblocks, nchunks):
+    def __init__(self, vt, it, nrows, ncols, indptr, indices, data, nblocks, nchunks, full=None):
         self.nrows, self.ncols, self.nblocks = nrows, ncols, nblocks
+        self.full = full          # the un-chunked column-blocked operand (ColBlock) of the same rows
         nchunks = max(1, min(int(nchunks), nrows))
         step = -(-nrows // nchunks)
         step += step & 1                      # even chunk starts keep y slices 16-byte aligned
@@ -300,11 +306,16 @@ class HostPipe:
         self.y_dev = torch.empty(nrows, dtype=data.dtype, device=dev)
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
-        # launch order: chunk c / block b at key c + b * lag; ties finish chunks first
         nc = len(self.chunks)
-        lag = max(1, nc // nblocks)
-        self.order = sorted(((c, b) for c in range(nc) for b in range(nblocks)),
-                            key=lambda cb_: (cb_[0] + cb_[1] * lag, -cb_[1]))
+        if full is not None:
+            # only the LAST column block decides when a row of y is final: blocks 0..nb-2 run as single
+            # launches over all rows (fewer launches, no per-chunk ramp), the last block chunk by chunk
+            self.order = [(-1, b) for b in range(nblocks - 1)] + [(c, nblocks - 1) for c in range(nc)]
+        else:
+            # launch order: chunk c / block b at key c + b * lag; ties finish chunks first
+            lag = max(1, nc // nblocks)
+            self.order = sorted(((c, b) for c in range(nc) for b in range(nblocks)),
+                                key=lambda cb_: (cb_[0] + cb_[1] * lag, -cb_[1]))
 
     def run(self, x_host: torch.Tensor, y_host: torch.Tensor):
         cur = torch.cuda.current_stream()
@@ -323,14 +334,21 @@ class HostPipe:
         waited = [False] * nb
         done_blocks = [0] * len(self.chunks)
         for (c, b) in self.order:
-            c0, c1, _, cb = self.chunks[c]
             if not waited[b]:
                 cur.wait_event(ev_x[b])
                 waited[b] = True
+            if c < 0:                      # a whole-matrix launch of an early column block
+                self.full.spmv_part(b, self.x_dev, self.y_dev)
+                for i in range(len(done_blocks)):
+                    done_blocks[i] += 1
+                continue
+            c0, c1, _, cb = self.chunks[c]
             y_c = self.y_dev[c0:c1]
             if cb is None:
                 if b == 0:
                     y_c.zero_()
+            elif self.full is not None:
+                cb.spmv_part_accumulate(b, self.x_dev, y_c)
             else:
                 cb.spmv_part(b, self.x_dev, y_c)
             done_blocks[c] += 1

@@ -426,7 +426,7 @@ class csr_array(CompressedBase):
             cb = self._colblock(blk)
             nchunks = int(os.environ.get("LEGATE_SPARSE_HOSTPIPE_CHUNKS", "8"))
             hp = HostPipe(vt_enum(self.dtype), blk.itype, blk.nrows, self.shape[1], blk.indptr, blk.indices,
-                          blk.data, cb.nblocks, nchunks)
+                          blk.data, cb.nblocks, nchunks, full=cb)
             blk.hostpipe = hp
         return hp
 

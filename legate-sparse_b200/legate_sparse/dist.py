@@ -77,6 +77,18 @@ def nnz_balanced_bounds(indptr, nparts: int) -> np.ndarray:
     return np.maximum.accumulate(b)
 
 
+def weight_balanced_bounds(weights, nparts: int) -> np.ndarray:
+    """Row boundaries with ~equal total weight per part (weights: per-row work, e.g. the number of
+    intermediate products of an SpGEMM row) — the generalisation of nnz_balanced_bounds."""
+    w = weights.detach().to(torch.float64).cpu().numpy() if isinstance(weights, torch.Tensor) else np.asarray(weights, dtype=np.float64)
+    nrows = w.shape[0]
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    targets = np.arange(1, nparts, dtype=np.float64) * (cum[-1] / float(nparts))
+    cuts = np.searchsorted(cum, targets, side="left").astype(np.int64)
+    b = np.concatenate([[0], np.clip(cuts, 0, nrows), [nrows]]).astype(np.int64)
+    return np.maximum.accumulate(b)
+
+
 # ---------------------------------------------------------------------------- collectives
 def allgather_rows(local: torch.Tensor, bounds: Sequence[int]) -> torch.Tensor:
     """Gather the row blocks ``local`` (this rank owns rows bounds[rank]:bounds[rank+1])
