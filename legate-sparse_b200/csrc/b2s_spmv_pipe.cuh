@@ -108,14 +108,14 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
   uint64_t* empty_bar = full_bar + STAGES;
   __shared__ V wsum[kPipeConsumers / 32];  // DOT only
   constexpr int LRCAP = LONGROWS ? TILE / 32 + 2 : 1;
-  __shared__ int lr_count[NG][2];
-  __shared__ int lr_list[NG][2][LRCAP];     // deferred rows (index inside the tile), per group and tile parity
+  __shared__ int lr_count[NG][3];
+  __shared__ int lr_list[NG][3][LRCAP];     // deferred rows (index inside the tile), per group; 3 slots in rotation
 
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ROWWALK ? kPipeConsumers : GT); }
     fence_mbar_init();
-    for (int g = 0; g < NG; ++g) { lr_count[g][0] = 0; lr_count[g][1] = 0; }
+    for (int g = 0; g < NG; ++g) { lr_count[g][0] = 0; lr_count[g][1] = 0; lr_count[g][2] = 0; }
   }
   __syncthreads();
 
@@ -224,6 +224,23 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
       const int lanes = lanes_for(nr, GT);
       const int groups = GT / lanes;
       const int gl = gtid & (lanes - 1);
+      const int slot = (int)((i / NG) % 3);
+      if constexpr (LONGROWS) {
+        // rows longer than 32 x lanes go on the tile's long-row list NOW (the row pointers are
+        // already staged): the group barrier after the products then covers the list as well
+        if (lanes < 32 && gl == 0) {
+          for (int64_t base = 0; base < nr; base += groups) {
+            const int64_t r = r_begin + base + gtid / lanes;
+            if (base + gtid / lanes < nr && r < nrows) {
+              int64_t lo_g, hi_g;
+              if (meta.rows_staged) { lo_g = srptr[r - meta.ra]; hi_g = srptr[r - meta.ra + 1]; }
+              else                  { lo_g = indptr[r];          hi_g = indptr[r + 1]; }
+              if (min(hi_g, E) - max(lo_g, S) > 32 * lanes)
+                lr_list[grp][slot][atomicAdd(&lr_count[grp][slot], 1)] = (int)(base + gtid / lanes);
+            }
+          }
+        }
+      }
       if (meta.full_tile) {
         // Gathers are issued in batches of BCH chunks = 4 gathers per thread.  Measured on the
         // column-blocked C2 matrix (profiles/r2_pipe_sweep.txt): all 8 of a thread at once 2.40 ms,
@@ -272,8 +289,10 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         }
       }
       if constexpr (NG == 1) consumer_bar_sync(); else group_bar_sync<GT>(grp);
-      const int slot = (int)((i / NG) & 1);
-      if (LONGROWS && gtid == 0) lr_count[grp][slot ^ 1] = 0;   // every warp of the group left the previous tile
+      // slot of the group's PREVIOUS tile = slot of its tile after next: every warp has left the
+      // previous tile (it is past this barrier), and nobody appends for the tile after next before
+      // the NEXT barrier, which this thread reaches only after this store
+      if (LONGROWS && gtid == 0) lr_count[grp][(slot + 2) % 3] = 0;
       auto finish_row = [&](int64_t r, int64_t lo_g, V sum, V yold) {
         bool wrote = false;
         if (lo_g < S) { head[t] = sum; wrote = true; }
@@ -295,9 +314,8 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         const int lo = (int)(max(lo_g, S) - S);
         int hi = (int)(min(hi_g, E) - S);
         bool defer = false;
-        if (LONGROWS && lanes < 32 && hi - lo > 32 * lanes) {   // uniform over the lane group
+        if (LONGROWS && lanes < 32 && hi - lo > 32 * lanes) {   // uniform over the lane group; on the list already
           defer = true;
-          if (gl == 0) lr_list[grp][slot][atomicAdd(&lr_count[grp][slot], 1)] = (int)(base + gtid / lanes);
           hi = lo;   // nothing to add here; every lane still takes part in the shuffles below
         }
         V s0 = zero_of<V>(), s1 = zero_of<V>();
@@ -312,8 +330,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         if (valid && gl == 0 && !defer) finish_row(r, lo_g, sum, (accumulate && base != 0) ? y[r] : ypre);
       }
       if constexpr (LONGROWS) {
-        if constexpr (NG == 1) consumer_bar_sync(); else group_bar_sync<GT>(grp);   // the list of this tile is complete
-        const int nlong = lr_count[grp][slot];
+        const int nlong = lr_count[grp][slot];   // complete since the barrier above
         const int wid = gtid >> 5, lane = gtid & 31;
         for (int e = wid; e < nlong; e += GT / 32) {
           const int64_t r = r_begin + lr_list[grp][slot][e];
