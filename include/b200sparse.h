@@ -246,6 +246,10 @@ int b2s_allreduce_board(b2s_dtype vt, void* inout, void* const* boards, int rank
  *             (synchronises the stream);
  *   numeric : fills c_indices (sorted within each row, like cuSPARSE) and c_data.
  * A block of rows of A may be passed (row-block partition); B is whole.
+ * Reproducibility: the structure (c_indptr, c_indices) is deterministic; the VALUES are accumulated
+ * with floating-point atomics (hash tables in shared memory, dense accumulators in HBM), so their
+ * summation order — and the last bits of c_data — may differ from run to run (SpMV and the CG /
+ * GMRES kernels have no such atomics and are bit-reproducible).
  * ---------------------------------------------------------------------- */
 int64_t b2s_spgemm_workspace_bytes(int64_t nrowsA, int64_t nnzA, int64_t ncolsB);
 
