@@ -264,6 +264,22 @@ template <> __device__ __forceinline__ c128 ld_gather_na<c128>(const c128* p, ui
   return r;
 }
 
+// result stores of the streaming kernels: written once, not re-read by this launch — evict_first in
+// L2 so that y (as large as x) does not compete with the x vector for L2 capacity
+template <typename T> __device__ __forceinline__ void st_stream(T* p, T v, uint64_t pol);
+template <> __device__ __forceinline__ void st_stream<float>(float* p, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+template <> __device__ __forceinline__ void st_stream<double>(double* p, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+template <> __device__ __forceinline__ void st_stream<c64>(c64* p, c64 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.re), "f"(v.im), "l"(pol) : "memory");
+}
+template <> __device__ __forceinline__ void st_stream<c128>(c128* p, c128 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.re), "d"(v.im), "l"(pol) : "memory");
+}
+
 // L2-coherent load of a value written by another CTA (bypasses L1)
 template <typename A>
 __device__ __forceinline__ A ld_cg(const A* p) {

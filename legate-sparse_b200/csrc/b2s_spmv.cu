@@ -375,16 +375,20 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   int nb = blocks_per_sm[dev].load(std::memory_order_acquire);
   if (nb <= 0) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // Resident CTAs / shared-memory carve-out of the products consumer, measured on C2 (random,
-    // column-blocked), the 4096^2 Laplacian and the power-law matrix (profiles/r2_occ_sweep.txt):
-    //   4-stage ring, 3 CTAs/SM (173 KB of shared memory, carve-out 80 %): 2.20 / 0.275 / 0.568 ms
-    //   4-stage ring, 2 CTAs/SM (carve-out 55 %, L1 = 124 KB)            : 2.32 / 0.357 / 0.505 ms
-    //   2-stage ring, 3 CTAs/SM (carve-out 44 %)                         : 2.60 / 0.364 / 0.488 ms
-    // Round 1 preferred 2 CTAs + a large L1 because its gathers allocated L1 lines; with
-    // L1::no_allocate gathers the third CTA wins.  The long-row (power-law) instances run the
-    // shallow ring.  B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
+    // Resident CTAs / ring depth / shared-memory carve-out of the products consumer, measured on C2
+    // (random, column-blocked), the 4096^2 Laplacian and the power-law matrix
+    // (profiles/r2_occ_sweep.txt, r2_occ_sweep2.txt; 1024-nnz tiles, ms):
+    //   3-stage ring, 3 CTAs/SM (130 KB of shared memory, carve-out 57 %, L1 = 124 KB): 2.13 / 0.277 / 0.534
+    //   4-stage ring, 3 CTAs/SM (173 KB, carve-out 80 %, L1 = 60 KB)                  : 2.20 / 0.275 / 0.568
+    //   4-stage ring, 2 CTAs/SM (carve-out 55 %)                                      : 2.32 / 0.357 / 0.505
+    //   2-stage ring, 3 CTAs/SM (carve-out 44 %)                                      : 2.60 / 0.364 / 0.488
+    // Round 1 ran 2 CTAs: its gathers allocated L1 lines and a third CTA cost more L1 than it hid
+    // latency.  With L1::no_allocate gathers the third CTA wins, and 3 stages leave it the large L1.
+    // The long-row (power-law) instances run the shallow ring (their gathers miss L2 19 % of the time;
+    // the larger L1 = more requests in flight matters more there than prefetch depth).
+    // B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
     int carve = -1, cap = 0;
-    if (!WINDOW) { cap = 3; carve = LONGROWS ? 50 : 80; }
+    if (!WINDOW) { cap = 3; carve = LONGROWS ? 50 : (TILE == 1024 ? 57 : 80); }
     carve = env_int("B2S_SPMV_CARVEOUT", carve);
     cap = env_int("B2S_SPMV_CTAS", cap);
     if (carve >= 0) B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -426,7 +430,7 @@ static int launch_pipe_tile(const PlanHeader* P, const int64_t* indptr, const I*
       return launch_pipe_inst<V, I, TILE, 2, false, false, false, 2, true>(P, indptr, cols, vals, x, y, dot_partials, w,
                                                                           npartials, peers, accumulate, st);
   }
-  if constexpr (TILE == 1024) return bcast ? B2S_PIPE(4, false, true, 2) : B2S_PIPE(4, false, false, 2);
+  if constexpr (TILE == 1024) return bcast ? B2S_PIPE(3, false, true, 2) : B2S_PIPE(3, false, false, 2);
   else                        return bcast ? B2S_PIPE(2, false, true, 2) : B2S_PIPE(2, false, false, 2);
 #undef B2S_PIPE
 }

@@ -16,7 +16,7 @@
 //                 its (col,val) pairs in shared memory, reads x from the staged window, accumulates
 //                 in registers, shuffle-reduces in a fixed order and writes y.  No CTA-wide barrier.
 //       products  (x gathered from L2): the consumers form NG independent groups of 256/NG threads
-//                 that take the CTA's tiles in turn (group g owns ring stages s = g mod NG), so that
+//                 that take the CTA's tiles in turn (tile i: group i mod 2, ring stage i mod 3), so that
 //                 one group's gather phase overlaps the other's reduction phase.  Every thread issues
 //                 all of its gathers at once for 16-byte chunks of the staged (col,val) slices
 //                 (conflict-free LDS/STS), parks the products in place, and after the group's named
@@ -81,7 +81,8 @@ template <typename I, int C> struct alignas((sizeof(I) * C) < 16 ? (sizeof(I) * 
 // all others the products consumer (each measured fastest there; the cross combinations were never
 // faster and are not instantiated).  BCAST compiles the peer stores in; the plain instances carry
 // no trace of them (the peer ranges cost the banded kernel 13% when they were a runtime branch).
-// NG = consumer groups of the products consumer (1 or 2; STAGES must be a multiple of NG).
+// NG = consumer groups of the products consumer (1 or 2; tile i of the CTA uses ring stage i % STAGES and
+// is consumed by group i % NG, whose GT threads are the arrivals its "empty" barrier expects).
 // LONGROWS (products consumer, skewed row lengths — power-law matrices): rows of the tile longer than
 // 32 x (lanes per row) are not summed by their small lane group (one lane walking a 1000-entry row
 // stalls its whole group at the next barrier: 41 % barrier stalls on BASELINE config 5) but
@@ -101,7 +102,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
   constexpr int T = L::T;
   constexpr bool ROWWALK = WINDOW;
   constexpr int GT = kPipeConsumers / NG;          // threads per consumer group
-  static_assert(STAGES % NG == 0 && (NG == 1 || !WINDOW), "bad consumer grouping");
+  static_assert(STAGES >= NG && (NG == 1 || !WINDOW), "bad consumer grouping");
   constexpr size_t STAGE = L::stage_bytes(WINDOW);
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + STAGE * STAGES);
@@ -298,7 +299,9 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         if (lo_g < S) { head[t] = sum; wrote = true; }
         else if (r < r_last || lo_g < E) {
           if (accumulate) sum = vadd(sum, yold);   // y += A_b x : later column blocks
-          if constexpr (BCAST) store_bcast(y, peers, r, sum); else y[r] = sum;
+          if constexpr (BCAST) store_bcast(y, peers, r, sum);
+          else if (l1_alloc) y[r] = sum;                        // the next kernel (CG) re-reads y: let it stay in L2
+          else st_stream<V>(y + r, sum, pol_stream);            // gather-bound class: y must not displace x in L2
           wrote = true;
         }
         if (DOT && wrote) dot_acc = vfma(w[r], sum, dot_acc);
