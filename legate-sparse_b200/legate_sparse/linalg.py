@@ -397,165 +397,199 @@ def cg_profile():
     return [(n, e0.elapsed_time(e1)) for (n, e0, e1) in _cg_profile]
 
 
+class _CgState:
+    """Buffers, halo ranges, exchange boards and CUDA graphs of the fused CG iteration for one
+    (matrix block, dtype, world size, graph length).  Cached on the matrix (`A._cg_state`): a second
+    solve with the same operator replays the captured graphs from its first iteration on and pays no
+    set-up (time-stepping codes solve with one matrix many times; the bench's wall clock then
+    measures iterations, not graph capture)."""
+
+    def __init__(self, A, dtype, nper):
+        from . import _device as D
+
+        self.G = G = dist.world_size()
+        self.n = n = A.shape[0]
+        self.blk = blk = A._block()
+        self.bounds = A.row_bounds()
+        self.dtype, self.nper = dtype, nper
+        self.key = (id(blk), np.dtype(dtype), G, nper)
+        r0, r1 = blk.r0, blk.r1
+        self.plan = A._plan(blk)
+        self.ncols = A.shape[1]
+        self.vt = D.vt_enum(dtype)
+        self.pv = dist.symm_vector(n, D.torch_dtype(dtype), "cg_p") if G > 1 else None
+        self.halo, self.peer_ptrs = None, None
+        if self.pv is not None:
+            self.p_full = self.pv.t      # replicated p lives in symmetric memory: peers store into it
+            self.p_full.zero_()
+            self.pv.barrier()
+            self.peer_ptrs = self.pv.peer_ptrs(r0)
+            # halo exchange: peer g only needs the part of my p block inside the [min col, max col]
+            # image of ITS rows (banded / stencil matrices: a few boundary rows instead of the block)
+            if not isinstance(self.peer_ptrs, tuple) and os.environ.get("LEGATE_SPARSE_NO_HALO", "0") in ("0", ""):
+                cr = torch.tensor(list(blk.colrange()), dtype=torch.int64, device=self.p_full.device)
+                allcr = torch.empty(2 * G, dtype=torch.int64, device=self.p_full.device)
+                torch.distributed.all_gather_into_tensor(allcr, cr)
+                allcr = allcr.cpu().numpy().reshape(G, 2)
+                lo, hi = [], []
+                for g in range(G):
+                    if g == dist.rank():
+                        continue
+                    a, b = max(int(allcr[g, 0]), r0), min(int(allcr[g, 1]) + 1, r1)
+                    lo.append(max(a - r0, 0))
+                    hi.append(max(b - r0, 0) if b > a else 0)
+                    if b <= a:
+                        lo[-1], hi[-1] = 1, 0          # empty: this peer never reads my block
+                sent = sum(max(h - l, 0) for l, h in zip(lo, hi))
+                if sent < (G - 1) * (r1 - r0):          # otherwise every peer needs everything
+                    self.halo = (lo, hi)
+        else:
+            self.p_full = D.zeros(n, dtype)
+        self.p_loc = self.p_full[r0:r1]
+        self.q = D.empty(r1 - r0, dtype)
+        self.x_loc = D.empty(r1 - r0, dtype)
+        self.r = D.empty(r1 - r0, dtype)
+        self.rho, self.rho1 = D.zeros(1, dtype), D.zeros(1, dtype)
+        self.pq, self.rr = D.zeros(1, dtype), D.zeros(1, dtype)
+        # cross-GPU scalar sums: in-kernel exchange through peer-mapped boards (one one-warp kernel
+        # each, summed in rank order) instead of NCCL all-reduces; channel 0 doubles as the "every p
+        # block has landed" barrier.  One sync point per dependency, no NCCL node in the graph.
+        self.board = dist.scalar_board() if (G > 1 and self.pv is not None) else None
+        self.token = D.zeros(1, dtype) if self.board is not None else None
+        self.red_ws = D.new_reduce_ws()   # owned by this state: never allocated inside a graph capture
+        self.graph1 = self.graphN = None
+        self.graph_failed = False
+
+    def body(self):
+        """one CG iteration on fixed buffers (capturable in a CUDA graph)"""
+        from . import _device as D
+
+        blk, G = self.blk, self.G
+        if self.pv is not None:
+            # no barrier needed before overwriting p_full: the reduction of rr at the end of the
+            # previous iteration already orders every rank's SpMV (the reader of p_full) before this point
+            if self.halo is not None:
+                D.cg_pupdate_halo(self.p_loc, self.r, self.rho, self.rho1, self.peer_ptrs, self.halo[0], self.halo[1])
+            else:
+                D.cg_pupdate_bcast(self.p_loc, self.r, self.rho, self.rho1, self.peer_ptrs)   # p block → every rank
+            if self.board is not None:
+                self.board.allreduce(self.token, 0)               # all blocks have landed (flag exchange)
+            else:
+                self.pv.barrier()
+        else:
+            D.cg_pupdate(self.p_loc, self.r, self.rho, self.rho1)
+            if G > 1:
+                dist.allgather_into(self.p_full, self.bounds)
+        if self.plan is not None:
+            D.spmv_dot(self.vt, blk.itype, blk.nrows, self.ncols, blk.nnz, blk.indptr, blk.indices, blk.data,
+                       self.p_full, self.q, self.p_loc, self.plan, self.pq)
+        else:  # empty block
+            self.q.zero_()
+            self.pq.zero_()
+        if self.board is not None:
+            self.board.allreduce(self.pq, 1)
+        else:
+            dist.allreduce_sum_(self.pq)
+        D.cg_update(self.x_loc, self.r, self.p_loc, self.q, self.rho, self.pq, self.rr, ws=self.red_ws)
+        if self.board is not None:
+            self.board.allreduce(self.rr, 2, cur_out=self.rho, prev_out=self.rho1)   # rho1 <- rho ; rho <- sum(rr)
+        else:
+            dist.allreduce_sum_(self.rr)
+            self.rho1.copy_(self.rho)   # old rho → rho1 ; new rho = rr  (z == r)
+            self.rho.copy_(self.rr)
+
+    def capture(self, want_n):
+        """CUDA graphs of the body: one iteration, and `nper` iterations back to back (between two
+        convergence tests the host has nothing to say, so one replay = 25 iterations and the loop is
+        insensitive to host-side jitter).  The collectives of the body are captured with it."""
+        if self.graph_failed:
+            return
+        try:
+            if self.graph1 is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.body()
+                self.graph1 = g
+            if want_n and self.graphN is None and self.nper > 1:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(self.nper):
+                        self.body()
+                self.graphN = g
+        except Exception as e:  # pragma: no cover - depends on driver / NCCL capture support
+            warnings.warn(f"CUDA graph capture of the CG iteration failed ({e}); running eagerly")
+            self.graph1 = self.graphN = None
+            self.graph_failed = True
+            torch.cuda.synchronize()
+
+
 def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, numpy_mode):
     """Identity-preconditioned CG on row-block-local vectors with fused kernels.
 
     Per iteration (G = number of ranks):
-      p_loc  = r_loc + (rho/rho1) p_loc            cg_pupdate        (p_full all-gathered if G>1)
-      q_loc  = A_blk p_full ; pq = <p_loc, q_loc>   spmv_csr_dot      (+ all-reduce if G>1)
-      x_loc += a p_loc ; r_loc -= a q_loc ; rr=<r,r> cg_update         (+ all-reduce if G>1)
+      p_loc  = r_loc + (rho/rho1) p_loc            cg_pupdate        (+ halo stores to the peers if G>1)
+      q_loc  = A_blk p_full ; pq = <p_loc, q_loc>   spmv_csr_dot      (+ board exchange if G>1)
+      x_loc += a p_loc ; r_loc -= a q_loc ; rr=<r,r> cg_update         (+ board exchange if G>1)
     The next rho is rr (z == r for the identity preconditioner)."""
     from . import _device as D
     from .csr import _spmv_block
 
     G = dist.world_size()
-    n = A.shape[0]
+    nper = max(int(conv_test_iters), 1)
     blk = A._block()
-    bounds = A.row_bounds()
+    st = getattr(A, "_cg_state", None)
+    fresh = st is None or st.key != (id(blk), np.dtype(dtype), G, nper) or st.blk is not blk
+    if fresh:
+        st = _CgState(A, dtype, nper)
+        A._cg_state = st
+    bounds = st.bounds
     r0, r1 = blk.r0, blk.r1
-    plan = A._plan(blk)
-    vt = D.vt_enum(dtype)
     cplx = dtype.kind == "c"
 
-    # r = b - A x0
-    pv = dist.symm_vector(n, D.torch_dtype(dtype), "cg_p") if G > 1 else None
-    if pv is not None:
-        p_full = pv.t          # replicated p lives in symmetric memory: peers store into it
-        p_full.zero_()
-        pv.barrier()
-        peer_ptrs = pv.peer_ptrs(r0)
-        # halo exchange: peer g only needs the part of my p block inside the [min col, max col]
-        # image of ITS rows (banded / stencil matrices: a few boundary rows instead of the block)
-        halo = None
-        if not isinstance(peer_ptrs, tuple) and os.environ.get("LEGATE_SPARSE_NO_HALO", "0") in ("0", ""):
-            cr = torch.tensor(list(blk.colrange()), dtype=torch.int64, device=p_full.device)
-            allcr = torch.empty(2 * G, dtype=torch.int64, device=p_full.device)
-            torch.distributed.all_gather_into_tensor(allcr, cr)
-            allcr = allcr.cpu().numpy().reshape(G, 2)
-            lo, hi = [], []
-            for g in range(G):
-                if g == dist.rank():
-                    continue
-                a, b = max(int(allcr[g, 0]), r0), min(int(allcr[g, 1]) + 1, r1)
-                lo.append(max(a - r0, 0))
-                hi.append(max(b - r0, 0) if b > a else 0)
-                if b <= a:
-                    lo[-1], hi[-1] = 1, 0          # empty: this peer never reads my block
-            sent = sum(max(h - l, 0) for l, h in zip(lo, hi))
-            if sent < (G - 1) * (r1 - r0):          # otherwise every peer needs everything
-                halo = (lo, hi)
-    else:
-        p_full = D.zeros(n, dtype)
-    p_loc = p_full[r0:r1]
-    q = D.empty(r1 - r0, dtype)
-    x_loc = x[r0:r1] if G > 1 else x
-    if G > 1:
-        x_loc = x_loc.clone()
+    # r = b - A x0 ; the solve starts from rho1 = 0 (⇒ the first p update is p = r)
+    st.x_loc.copy_(x[r0:r1] if G > 1 else x)
     if bool(torch.any(x != 0).item()) if x.numel() else False:
-        _spmv_block(A, blk, x, q)
-        r = b_dev[r0:r1] - q
+        _spmv_block(A, blk, x, st.q)
+        torch.sub(b_dev[r0:r1], st.q, out=st.r)
     else:
-        r = b_dev[r0:r1].clone()
+        st.r.copy_(b_dev[r0:r1])
+    st.rho1.zero_()
+    D.dot(st.r, st.r, out=st.rho)
+    dist.allreduce_sum_(st.rho)
+    rho, r = st.rho, st.r
 
-    rho = D.zeros(1, dtype)
-    rho1 = D.zeros(1, dtype)   # 0 ⇒ first cg_pupdate does p = r
-    pq = D.zeros(1, dtype)
-    rr = D.zeros(1, dtype)
-    D.dot(r, r, out=rho)
-    dist.allreduce_sum_(rho)
-    # cross-GPU scalar sums: in-kernel exchange through peer-mapped boards (one one-warp kernel each,
-    # summed in rank order) instead of NCCL all-reduces; channel 0 doubles as the "every p block has
-    # landed" barrier.  Per iteration: ONE sync point per dependency, no NCCL node in the graph.
-    board = dist.scalar_board() if (G > 1 and pv is not None) else None
-    token = D.zeros(1, dtype) if board is not None else None
-    red_ws = D.new_reduce_ws()   # owned by this solve: never allocated inside a graph capture
-
-    def body():
-        """one CG iteration on fixed buffers (capturable in a CUDA graph)"""
-        if pv is not None:
-            # no barrier needed before overwriting p_full: the reduction of rr at the end of the
-            # previous iteration already orders every rank's SpMV (the reader of p_full) before this point
-            if halo is not None:
-                D.cg_pupdate_halo(p_loc, r, rho, rho1, peer_ptrs, halo[0], halo[1])   # boundary slices only
-            else:
-                D.cg_pupdate_bcast(p_loc, r, rho, rho1, peer_ptrs)   # p block → every rank (NVLink stores)
-            if board is not None:
-                board.allreduce(token, 0)                         # all blocks have landed (flag exchange)
-            else:
-                pv.barrier()
-        else:
-            D.cg_pupdate(p_loc, r, rho, rho1)
-            if G > 1:
-                dist.allgather_into(p_full, bounds)
-        if plan is not None:
-            D.spmv_dot(vt, blk.itype, blk.nrows, A.shape[1], blk.nnz, blk.indptr, blk.indices, blk.data,
-                       p_full, q, p_loc, plan, pq)
-        else:  # empty block
-            q.zero_()
-            pq.zero_()
-        if board is not None:
-            board.allreduce(pq, 1)
-        else:
-            dist.allreduce_sum_(pq)
-        D.cg_update(x_loc, r, p_loc, q, rho, pq, rr, ws=red_ws)
-        if board is not None:
-            board.allreduce(rr, 2, cur_out=rho, prev_out=rho1)   # rho1 <- rho ; rho <- sum(rr)  (z == r)
-        else:
-            dist.allreduce_sum_(rr)
-            rho1.copy_(rho)   # old rho → rho1 ; new rho = rr  (z == r)
-            rho.copy_(rr)
-
-    # CUDA graphs of the iteration body: one iteration, and `conv_test_iters` iterations back to back
-    # (between two convergence tests the host has nothing to say, so one replay = 25 iterations and
-    # the loop is insensitive to host-side jitter).  LEGATE_SPARSE_CG_GRAPH=0 disables them; the
-    # collectives of the body are captured with it.
+    # LEGATE_SPARSE_CG_GRAPH=0 disables the CUDA graphs
     mode = os.environ.get("LEGATE_SPARSE_CG_GRAPH", "1")
     want_graph = callback is None and mode != "0"
-    graph1 = graphN = None
-    nper = max(int(conv_test_iters), 1)
     prof = _cg_profile if os.environ.get("LEGATE_SPARSE_CG_PROFILE", "0") not in ("0", "") else None
     if prof is not None:
         prof.clear()
-
-    def capture(times):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(times):
-                body()
-        return g
+    iters = 0
 
     def run(k):
         """advance k iterations with as few launches as possible"""
-        nonlocal graph1, graphN, want_graph
         done = 0
         while done < k:
-            if want_graph and graph1 is None and iters + done >= 1:
-                # iteration 0 ran eagerly (lazy allocations, NCCL warm-up); capture now
-                try:
-                    torch.cuda.synchronize()
-                    graph1 = capture(1)
-                    if nper > 1 and maxiter - iters >= 2 * nper:
-                        graphN = capture(nper)
-                except Exception as e:  # pragma: no cover - depends on driver / NCCL capture support
-                    warnings.warn(f"CUDA graph capture of the CG iteration failed ({e}); running eagerly")
-                    graph1 = graphN = None
-                    want_graph = False
-                    torch.cuda.synchronize()
-            if graphN is not None and k - done >= nper:
+            if want_graph and (st.graph1 is None or (st.graphN is None and maxiter - iters >= 2 * nper)) \
+                    and (not fresh or iters + done >= 1) and not st.graph_failed:
+                # a fresh state runs iteration 0 eagerly (lazy allocations, NCCL warm-up) and captures then
+                st.capture(want_n=maxiter - iters >= 2 * nper)
+            if want_graph and st.graphN is not None and k - done >= nper:
                 ev = _prof_begin(prof)
-                graphN.replay()
+                st.graphN.replay()
                 _prof_end(prof, ev, nper)
                 done += nper
-            elif graph1 is not None:
+            elif want_graph and st.graph1 is not None:
                 ev = _prof_begin(prof)
-                graph1.replay()
+                st.graph1.replay()
                 _prof_end(prof, ev, 1)
                 done += 1
             else:
-                body()
+                st.body()
                 done += 1
 
-    iters = 0
     while iters < maxiter:
         if callback is not None:
             step = 1
@@ -568,8 +602,8 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
         run(step)
         iters += step
         if callback is not None:
-            xf = dist.allgather_rows(x_loc, bounds) if G > 1 else x_loc
-            callback(D.to_host(xf) if numpy_mode else xf)
+            xf = dist.allgather_rows(st.x_loc, bounds) if G > 1 else st.x_loc
+            callback(D.to_host(xf) if numpy_mode else xf.clone())
         if iters % conv_test_iters == 0 or iters == (maxiter - 1):
             if cplx:
                 nr2 = D.nrm2(r) ** 2
@@ -579,9 +613,10 @@ def _cg_fused(A, b_dev, x, dtype, atol, maxiter, callback, conv_test_iters, nump
                 rnorm = float(torch.sqrt(rho.abs()).item())
             if rnorm < atol:
                 break
-    if board is not None:
-        board.check()
-    x_out = dist.allgather_rows(x_loc, bounds) if G > 1 else x_loc
+    if st.board is not None:
+        st.board.check()
+    # the iterate lives in the cached state: hand out a copy
+    x_out = dist.allgather_rows(st.x_loc, bounds) if G > 1 else st.x_loc.clone()
     return x_out, iters
 
 
