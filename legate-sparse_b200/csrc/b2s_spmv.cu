@@ -369,42 +369,63 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   using L = PipeLayout<V, I, TILE>;
   const size_t smem = L::stage_bytes(WINDOW) * STAGES + 16 * STAGES;
   auto kern = spmv_pipe_kernel<V, I, TILE, STAGES, WINDOW, DOT, BCAST, NG, LONGROWS>;
-  // function attributes are per device: cache the resident-CTA count per (instantiation, device)
-  static std::atomic<int> blocks_per_sm[kMaxDevices];
+  // function attributes are per device: cache the largest resident-CTA count (registers / shared
+  // memory with the maximum carve-out) per (instantiation, device)
+  static std::atomic<int> max_blocks_per_sm[kMaxDevices];
   const int dev = current_device();
-  int nb = blocks_per_sm[dev].load(std::memory_order_acquire);
-  if (nb <= 0) {
+  int nb_max = max_blocks_per_sm[dev].load(std::memory_order_acquire);
+  if (nb_max <= 0) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // Resident CTAs / ring depth / shared-memory carve-out of the products consumer, measured on C2
-    // (random, column-blocked), the 4096^2 Laplacian and the power-law matrix
-    // (profiles/r2_occ_sweep.txt, r2_occ_sweep2.txt; 1024-nnz tiles, ms):
-    //   3-stage ring, 3 CTAs/SM (130 KB of shared memory, carve-out 57 %, L1 = 124 KB): 2.13 / 0.277 / 0.534
-    //   4-stage ring, 3 CTAs/SM (173 KB, carve-out 80 %, L1 = 60 KB)                  : 2.20 / 0.275 / 0.568
-    //   4-stage ring, 2 CTAs/SM (carve-out 55 %)                                      : 2.32 / 0.357 / 0.505
-    //   2-stage ring, 3 CTAs/SM (carve-out 44 %)                                      : 2.60 / 0.364 / 0.488
-    // Round 1 ran 2 CTAs: its gathers allocated L1 lines and a third CTA cost more L1 than it hid
-    // latency.  With L1::no_allocate gathers the third CTA wins, and 3 stages leave it the large L1.
-    // The long-row (power-law) instances run the shallow ring (their gathers miss L2 19 % of the time;
-    // the larger L1 = more requests in flight matters more there than prefetch depth).
-    // B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
-    int carve = -1, cap = 0;
-    if (!WINDOW) { cap = 3; carve = LONGROWS ? 50 : (TILE == 1024 ? 57 : 80); }
-    carve = env_int("B2S_SPMV_CARVEOUT", carve);
-    cap = env_int("B2S_SPMV_CTAS", cap);
-    if (carve >= 0) B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPipeThreads, smem));
-    if (nb < 1) { set_error("spmv_pipe_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
-    if (cap >= 1 && cap < nb) nb = cap;
-    blocks_per_sm[dev].store(nb, std::memory_order_release);
+    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, kern, kPipeThreads, smem));
+    if (nb_max < 1) { set_error("spmv_pipe_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
+    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault));
+    max_blocks_per_sm[dev].store(nb_max, std::memory_order_release);
   }
+  // Resident CTAs / ring depth / shared-memory carve-out (a per-LAUNCH attribute) of the products
+  // consumer, measured on C2 (random, column-blocked), the 4096^2 Laplacian and the power-law matrix
+  // (profiles/r2_occ_sweep.txt, r2_occ_sweep2.txt; 1024-nnz tiles, ms):
+  //   3-stage ring, 3 CTAs/SM (130 KB of shared memory, carve-out 57 %, L1 = 124 KB): 2.13 / 0.277 / 0.534
+  //   3-stage ring, 4 CTAs/SM (174 KB, carve-out 80 %, L1 = 60 KB)                  : 2.24 / 0.245 / 0.573
+  //   4-stage ring, 3 CTAs/SM (173 KB, carve-out 80 %)                              : 2.20 / 0.275 / 0.568
+  //   4-stage ring, 2 CTAs/SM (carve-out 55 %)                                      : 2.32 / 0.357 / 0.505
+  //   2-stage ring, 3 CTAs/SM (carve-out 44 %)                                      : 2.60 / 0.364 / 0.488
+  // Round 1 ran 2 CTAs: its gathers allocated L1 lines and a third CTA cost more L1 than it hid
+  // latency.  With L1::no_allocate gathers the third CTA wins and 3 stages leave it the large L1.
+  // L1-friendly matrices (near tiles: the gathers hit L1) take the fourth CTA.  The long-row
+  // (power-law) instances run the shallow ring: their gathers miss L2 19 % of the time and the
+  // larger L1 (= more requests in flight) matters more there than prefetch depth.
+  // B2S_SPMV_CARVEOUT (percent) / B2S_SPMV_CTAS override for sweeps.
+  const int l1_alloc = env_int("B2S_SPMV_L1_ALLOC", P->near_tiles * 2 >= P->ntiles ? 1 : 0) != 0;
+  int carve = -1, cap = 0;
+  if (!WINDOW) {
+    if (LONGROWS)                    { cap = 3; carve = 50; }
+    else if (l1_alloc && TILE == 1024) { cap = 4; carve = 80; }
+    else                             { cap = 3; carve = TILE == 1024 ? 57 : 80; }
+  }
+  carve = env_int("B2S_SPMV_CARVEOUT", carve);
+  cap = env_int("B2S_SPMV_CTAS", cap);
+  int nb = nb_max;
+  if (cap >= 1 && cap < nb) nb = cap;
   int64_t grid = (int64_t)nb * num_sms();
   if (grid > P->ntiles) grid = P->ntiles;
   *npartials = grid;
-  const int l1_alloc = env_int("B2S_SPMV_L1_ALLOC", P->near_tiles * 2 >= P->ntiles ? 1 : 0) != 0;
-  kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals,
-                                                   x, y, P->tile_row, P->tile_win,
-                                                   reinterpret_cast<V*>(P->head), dot_partials, w, peers,
-                                                   (accumulate ? 1 : 0) | (l1_alloc ? 2 : 0));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kPipeThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (carve >= 0) {
+    attr[0].id = cudaLaunchAttributePreferredSharedMemoryCarveout;
+    attr[0].val.sharedMemCarveout = (unsigned)carve;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  B2S_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals, x, y,
+                                  (const int64_t*)P->tile_row, (const int64_t*)P->tile_win,
+                                  reinterpret_cast<V*>(P->head), dot_partials, w, peers,
+                                  (accumulate ? 1 : 0) | (l1_alloc ? 2 : 0)));
   B2S_CHECK_LAUNCH();
   return B2S_OK;
 }

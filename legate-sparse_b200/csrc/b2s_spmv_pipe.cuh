@@ -88,7 +88,7 @@ template <typename I, int C> struct alignas((sizeof(I) * C) < 16 ? (sizeof(I) * 
 // stalls its whole group at the next barrier: 41 % barrier stalls on BASELINE config 5) but
 // deferred to a second pass where each gets a full warp.
 template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG, bool LONGROWS = false>
-__global__ void __launch_bounds__(kPipeThreads)
+__global__ void __launch_bounds__(kPipeThreads, (WINDOW || sizeof(V) > 8) ? 0 : 4)   // products: 4 CTAs/SM must fit the register file
 spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const int64_t* __restrict__ indptr, const I* __restrict__ cols,
                  const V* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
