@@ -389,7 +389,7 @@ def run_b200(args):
 
     # ---- gathered-y variant (what the public A @ x returns) at N>1, checked against the oracle
     if G > 1:
-        y_full = torch.empty(n, dtype=torch.float64, device=dev)
+        y_full = dist.replicated_empty(n, torch.float64)     # symmetric memory: the kernel stores into it directly
         g_ms, _ = timed_steps(lambda: A.dot(x, out=y_full), args.steps, args.warmup, dist)
         rows = torch.linspace(0, n - 1, 512, device=dev).long().unique()
         want = oracle_rows(rows.cpu().numpy(), n, k, x_np)
@@ -400,9 +400,10 @@ def run_b200(args):
         line["gathered"] = {"value": 2.0 * nnz_total / (g_ms / args.steps * 1e-3) / 1e9, "unit": UNIT,
                             "ms_per_step": g_ms / args.steps, "oracle_rows_checked": int(rows.numel()),
                             "oracle_relerr": gerr,
-                            "what": "SpMV with the all-gather of y fused into the kernel stores (NVLink P2P via symmetric "
-                                    "memory, double-buffered: one closing barrier; NCCL all-gather when peer memory is "
-                                    "unavailable) + copy into out; rows from EVERY rank's block checked against the oracle"}
+                            "what": "A.dot(x, out=dist.replicated_empty(n)): SpMV with the all-gather of y fused into the "
+                                    "kernel stores (NVLink P2P straight into every rank's copy of the caller's symmetric out "
+                                    "buffer, opening + closing barrier, no staging copy; NCCL all-gather when peer memory is "
+                                    "unavailable); rows from EVERY rank's block checked against the oracle"}
 
     if not args.no_extras:
         del A, blk

@@ -371,8 +371,8 @@ namespace b2s {
 constexpr int kBoardChannels = 4;
 constexpr int kBoardRanks    = kMaxPeers + 1;
 struct alignas(32) BoardSlot {
-  unsigned char value[16];
-  unsigned long long seq;
+  unsigned char value[16];      // packed form (values <= 8 bytes): bytes 0..7 payload, 8..15 sequence number
+  unsigned long long seq;       // c128 form: 16-byte value above, sequence number here
   unsigned long long pad;
 };
 struct BoardPtrs { BoardSlot* b[kBoardRanks]; };
@@ -386,8 +386,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
+// 16-byte slot accesses: {payload, seq} travel in ONE store / load, so no fence is needed between
+// the value and its flag (a 16-byte aligned vector access is a single transaction on NVLink and L2)
+__device__ __forceinline__ void st_slot16(void* p, unsigned long long payload, unsigned long long seq) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(payload), "l"(seq) : "memory");
+}
+__device__ __forceinline__ void ld_slot16(const void* p, unsigned long long* payload, unsigned long long* seq) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(*payload), "=l"(*seq) : "l"(p) : "memory");
+}
+
 // inout[0]: this rank's partial on entry, the global sum on exit.  prev_out (optional):
 // prev_out[0] = cur_out[0]; cur_out[0] = sum  (CG: rho1 <- rho, rho <- rr) — saves two copy kernels.
+// Values of up to 8 bytes (f32, f64, c64) are exchanged as {value, seq} pairs in one 16-byte store;
+// c128 uses the value + release/acquire flag form.
 template <typename V>
 __global__ void __launch_bounds__(32)
 allreduce_board_kernel(V* __restrict__ inout, const BoardPtrs boards, int rank, int nranks, int channel,
@@ -400,16 +411,31 @@ allreduce_board_kernel(V* __restrict__ inout, const BoardPtrs boards, int rank, 
   if (t < nranks) {
     const V mine = inout[0];
     BoardSlot* dst = boards.b[t] + slot_base + rank;          // my slot on rank t's board
-    *reinterpret_cast<V*>(dst->value) = mine;
-    st_release_sys(&dst->seq, seq);                           // value first, then the flag
     BoardSlot* src = boards.b[rank] + slot_base + t;           // rank t's slot on my board
     const long long t0 = clock64();
     bool ok = true;
-    while (ld_acquire_sys(&src->seq) != seq) {
-      if (clock64() - t0 > (1ll << 34)) { ok = false; break; }   // ~8 s: a peer died — do not hang the GPU
+    if constexpr (sizeof(V) <= 8) {
+      unsigned long long payload = 0;
+      memcpy(&payload, &mine, sizeof(V));
+      st_slot16(dst, payload, seq);                            // slot bytes 0..15 = {payload, seq}
+      unsigned long long got = 0, gseq = 0;
+      while (true) {
+        ld_slot16(src, &got, &gseq);
+        if (gseq == seq) break;
+        if (clock64() - t0 > (1ll << 34)) { ok = false; break; }   // ~8 s: a peer died — do not hang the GPU
+      }
+      V v;
+      memcpy(&v, &got, sizeof(V));
+      vals[t] = v;
+    } else {
+      *reinterpret_cast<V*>(dst->value) = mine;
+      st_release_sys(&dst->seq, seq);                           // value first, then the flag
+      while (ld_acquire_sys(&src->seq) != seq) {
+        if (clock64() - t0 > (1ll << 34)) { ok = false; break; }
+      }
+      vals[t] = *reinterpret_cast<const V*>(src->value);        // ordered after the acquire load above
     }
     if (!ok && err) atomicExch(err, 1);
-    vals[t] = *reinterpret_cast<const V*>(src->value);   // ordered after the acquire load above
   }
   __syncwarp();
   if (t == 0) {

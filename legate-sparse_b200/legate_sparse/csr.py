@@ -937,7 +937,15 @@ def spmv(A: csr_array, x, y=None):
         # collective decision (same on every rank): symmetric memory available or not.  Two buffers
         # are used in turn: the closing barrier of call k orders every peer's reads of buffer k%2
         # (call k-2's result) before anyone writes it again, so no opening barrier is needed.
-        sv = dist.symm_vector_alternating(n, torch_dtype(A.dtype), "spmv_y")
+        own = dist.symm_of(y) if y is not None else None
+        if own is not None:
+            # the caller's out= lives in symmetric memory (dist.replicated_empty): the kernel stores into
+            # every rank's copy of it directly.  The caller may reuse it call after call, so an opening
+            # barrier orders the peers' reads of the previous content before anyone overwrites it.
+            sv = own
+            sv.barrier()
+        else:
+            sv = dist.symm_vector_alternating(n, torch_dtype(A.dtype), "spmv_y")
         if sv is not None:
             # fused SpMV + all-gather: y stores go to every rank's replicated buffer over NVLink
             from ._device import spmv_bcast, vt_enum
@@ -955,7 +963,9 @@ def spmv(A: csr_array, x, y=None):
                     if g != dist.rank() and blk.nrows > 0:
                         sv.h.get_buffer(g, (n,), sv.t.dtype)[blk.r0 : blk.r1].copy_(local)
             sv.barrier()   # every block has landed everywhere
-            if y is not None and _is_dev(y) and y.is_contiguous():
+            if own is not None:
+                y_dev = y
+            elif y is not None and _is_dev(y) and y.is_contiguous():
                 y.copy_(sv.t)
                 y_dev = y
             else:

@@ -330,3 +330,30 @@ def scalar_board():
         return None
     _board = b
     return _board
+
+
+_user_symm: dict = {}
+
+
+def replicated_empty(n: int, dtype: torch.dtype):
+    """A length-n device vector in SYMMETRIC memory (mapped into every rank) for use as the ``out=`` of
+    ``A.dot(x, out=...)`` with several ranks: the SpMV kernel then stores its rows straight into
+    every rank's copy of THIS buffer and no staging copy is made (collective: every rank must call
+    it in the same order).  Falls back to a plain device tensor when peer memory is unavailable."""
+    if world_size() == 1 or not torch.cuda.is_available() or _symm_broken:
+        return torch.empty(int(n), dtype=dtype, device="cuda" if torch.cuda.is_available() else "cpu")
+    key = ("user", len(_user_symm))
+    sv = symm_vector(int(n), dtype, f"user{len(_user_symm)}")
+    if sv is None:
+        return torch.empty(int(n), dtype=dtype, device="cuda")
+    _user_symm[sv.t.data_ptr()] = sv
+    return sv.t
+
+
+def symm_of(t):
+    """The SymmVector behind a tensor handed out by replicated_empty (else None)."""
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        sv = _user_symm.get(t.data_ptr())
+        if sv is not None and sv.t.numel() == t.numel() and sv.t.dtype == t.dtype:
+            return sv
+    return None

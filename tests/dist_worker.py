@@ -115,6 +115,12 @@ def main():
     out_blk = torch.empty(blk.nrows, dtype=torch.float64).pin_memory()
     A.dot_local(torch.from_numpy(x).pin_memory(), out=out_blk)
     assert relerr(out_blk.numpy(), (S @ x)[blk.r0 : blk.r1]) < 1e-12
+    # caller-owned symmetric out buffer: the kernel stores into every rank's copy of it, no staging copy
+    yr = dist.replicated_empty(n, torch.float64)
+    xt = torch.from_numpy(x).cuda()
+    for s_ in (1.0, -2.0, 0.5):
+        got = A.dot(s_ * xt, out=yr)
+        assert got is yr and relerr(yr.cpu().numpy(), s_ * (S @ x)) < 1e-12
     # several calls in a row: the replicated result buffers alternate (no opening barrier)
     for s_ in (1.0, 2.0, 3.0, 4.0):
         assert relerr(A @ (s_ * x), s_ * (S @ x)) < 1e-12

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <string>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
 
@@ -80,6 +81,12 @@ __device__ __forceinline__ void bulk16(void* dst, const void* src, uint64_t* bar
 __device__ __forceinline__ double ldg_nc(const double* p) {
   double r; asm("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p)); return r;
 }
+__device__ __forceinline__ double ldg_na(const double* p) {
+  double r; asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p)); return r;
+}
+__device__ __forceinline__ double ldg_cg(const double* p) {
+  double r; asm("ld.global.cg.f64 %0, [%1];" : "=d"(r) : "l"(p)); return r;
+}
 __device__ __forceinline__ double2 ldg_nc2(const double* p) {
   double2 r; asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p)); return r;
 }
@@ -119,6 +126,30 @@ __global__ void __launch_bounds__(256) k_lsu(int64_t nnz, const int* __restrict_
   for (; i + 3 < nnz; i += stride) {
     int4 c = ldg_stream4(cols + i);
     acc += ldg_nc(x + c.x) + ldg_nc(x + c.y) + ldg_nc(x + c.z) + ldg_nc(x + c.w);
+  }
+  block_sum_to(acc, out);
+}
+
+// load flavours of the LSU path: MODE 0 = ld.global.nc, 1 = nc + L1::no_allocate, 2 = ld.global.cg
+template <int MODE, int INFLIGHT>
+__global__ void __launch_bounds__(256) k_lsu_mode(int64_t nnz, const int* __restrict__ cols, const double* __restrict__ x, double* out) {
+  double acc = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  constexpr int U = INFLIGHT / 4;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  for (; i + (U - 1) * stride + 3 < nnz; i += stride * U) {
+    int4 c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = ldg_stream4(cols + i + u * stride);
+    double v[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int cc[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[u][k] = MODE == 0 ? ldg_nc(x + cc[k]) : (MODE == 1 ? ldg_na(x + cc[k]) : ldg_cg(x + cc[k]));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
   }
   block_sum_to(acc, out);
 }
@@ -361,6 +392,20 @@ int main(int argc, char** argv) {
   run("lsu   ld.global.nc.f64  unroll 4 (16 in flight)", nnz, iters, ref_sum, [&] { k_lsu<4, false><<<148 * 8, 256>>>(nnz, cols, x, d_out); });
   run("lsu   unroll 2, 4 CTAs/SM", nnz, iters, ref_sum, [&] { k_lsu<2, false><<<148 * 4, 256>>>(nnz, cols, x, d_out); });
   run("lsu16 ld.global.nc.v2.f64 unroll 2", nnz, iters, ref_sum, [&] { k_lsu<2, true><<<148 * 8, 256>>>(nnz, cols, x, d_out); });
+
+  // ---- load flavours x requests in flight x CTAs/SM (matters when x misses L2: run with xmb = 64 / 160)
+  if (getenv("GATHER_FLAVOURS")) {
+    const char* fl[3] = {"nc", "nc.L1::no_allocate", "cg"};
+    for (int ctas : {4, 8}) {
+      run((std::string("lsu ") + fl[0] + "  4 in flight, CTAs/SM=" + std::to_string(ctas)).c_str(), nnz, iters, ref_sum, [&] { k_lsu_mode<0, 4><<<148 * ctas, 256>>>(nnz, cols, x, d_out); });
+      run((std::string("lsu ") + fl[1] + "  4 in flight, CTAs/SM=" + std::to_string(ctas)).c_str(), nnz, iters, ref_sum, [&] { k_lsu_mode<1, 4><<<148 * ctas, 256>>>(nnz, cols, x, d_out); });
+      run((std::string("lsu ") + fl[2] + "  4 in flight, CTAs/SM=" + std::to_string(ctas)).c_str(), nnz, iters, ref_sum, [&] { k_lsu_mode<2, 4><<<148 * ctas, 256>>>(nnz, cols, x, d_out); });
+      run((std::string("lsu ") + fl[0] + " 16 in flight, CTAs/SM=" + std::to_string(ctas)).c_str(), nnz, iters, ref_sum, [&] { k_lsu_mode<0, 16><<<148 * ctas, 256>>>(nnz, cols, x, d_out); });
+      run((std::string("lsu ") + fl[1] + " 16 in flight, CTAs/SM=" + std::to_string(ctas)).c_str(), nnz, iters, ref_sum, [&] { k_lsu_mode<1, 16><<<148 * ctas, 256>>>(nnz, cols, x, d_out); });
+      run((std::string("lsu ") + fl[2] + " 16 in flight, CTAs/SM=" + std::to_string(ctas)).c_str(), nnz, iters, ref_sum, [&] { k_lsu_mode<2, 16><<<148 * ctas, 256>>>(nnz, cols, x, d_out); });
+    }
+    return 0;
+  }
 
   // ---- TMA gather4: tensor map over x as [ncols/2][2] fp64
   EncodeTiled_t encode = nullptr;
