@@ -200,7 +200,7 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_spmv_full(n, k, budget_s, warm=1):
+def cpu_spmv_full(n, k, budget_s, warm=1, x=None):
     """The reference's OpenMP task body (spmv_omp.cc:36-44, oracle/ref_kernels.c) on the FULL bench
     matrix regenerated by the host twin of legate_sparse.random (same seed → same matrix; arrays
     first-touched by the threads that use them).  Best over {all threads, half}."""
@@ -210,7 +210,8 @@ def cpu_spmv_full(n, k, budget_s, warm=1):
     oracle.omp_set_threads(threads_all)
     t0 = time.perf_counter()
     indptr, cols, vals = oracle.random_csr(n, n, n * k, SEED)
-    x = oracle.fill_uniform(n, 1)
+    if x is None:
+        x = oracle.fill_uniform(n, 1)
     gen_s = time.perf_counter() - t0
     best, y = None, None
     for threads in sorted({threads_all, max(1, threads_all // 2)}, reverse=True):
@@ -283,12 +284,12 @@ def run_b200(args):
     A = sparse.random(n, n, density=k / n, rng=SEED, dtype=np.float64)
     blk = A._block()
     vals, cols, indptr = blk.data, blk.indices, blk.indptr
-    # x: the host twin's stream (so that the CPU arm multiplies the same vector), uploaded once
-    from oracle import oracle  # input generation for the parity legs only; never inside a timed region
-
-    x_np = oracle.fill_uniform(n, 1)
-    x_host = torch.from_numpy(x_np).pin_memory()
-    x = x_host.to(dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    x = torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    x_host.copy_(x)
+    x_np = x_host.numpy()          # the checker legs (oracle rows, CPU baseline) multiply the same vector
     y_loc = torch.empty(r1 - r0, dtype=torch.float64, device=dev)
     t_build = time.perf_counter()
     A.dot_local(x, out=y_loc)  # builds the plan / column-blocked operand (one-time, like Legate's cached partitions)
@@ -416,7 +417,7 @@ def run_b200(args):
         line["spgemm"] = spgemm_leg(args, dist, dev, rank)
         if G == 1 and rank == 0:
             line["cusparse"] = cusparse_leg(vals, cols, indptr, x, n, args)
-            line["cpu_baseline"] = cpu_baseline_leg(args, y_loc)
+            line["cpu_baseline"] = cpu_baseline_leg(args, y_loc, x_np)
     line["clocks"] = clocks.stop()   # sampled from the first timed region to the last one
     if rank == 0:
         print(json.dumps(line))
@@ -781,13 +782,13 @@ def cusparse_leg(vals, cols, indptr, x, n, args):
         return {"unavailable": str(e)[:200]}
 
 
-def cpu_baseline_leg(args, y_gpu):
+def cpu_baseline_leg(args, y_gpu, x_np):
     """Oracle port of the reference's OpenMP task on the host cores, FULL matrix (about 10-20 s incl.
     generating it), and the GPU's y checked against the CPU's y on ALL rows."""
     import scipy.sparse as sp
 
     k, n = args.nnz_per_row, args.rows
-    info, (indptr, cols, vals, x, y_cpu) = cpu_spmv_full(n, k, budget_s=8.0)
+    info, (indptr, cols, vals, x, y_cpu) = cpu_spmv_full(n, k, budget_s=8.0, x=np.ascontiguousarray(x_np))
     dt = info["seconds_per_spmv"]
     yg = y_gpu.cpu().numpy()
     err = float(np.linalg.norm(yg - y_cpu) / np.linalg.norm(y_cpu))

@@ -317,28 +317,32 @@ class HostPipe:
             self.order = sorted(((c, b) for c in range(nc) for b in range(nblocks)),
                                 key=lambda cb_: (cb_[0] + cb_[1] * lag, -cb_[1]))
 
-    def run(self, x_host: torch.Tensor, y_host: torch.Tensor):
+    def run(self, x_host, y_host: torch.Tensor, x_dev=None):
+        """x_host: host vector uploaded slice by slice — or None with `x_dev` already complete on the
+        device (several ranks: the slices were all-gathered over NVLink); y_host: host result."""
         cur = torch.cuda.current_stream()
         self.h2d.wait_stream(cur)          # earlier readers of x_dev / y_dev are done
         self.d2h.wait_stream(cur)
         bw, nb = self.block_cols, self.nblocks
         ev_x = []
-        with torch.cuda.stream(self.h2d):
-            for b in range(nb):
-                lo, hi = b * bw, min((b + 1) * bw, self.ncols)
-                if hi > lo:
-                    self.x_dev[lo:hi].copy_(x_host[lo:hi], non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(self.h2d)
-                ev_x.append(e)
-        waited = [False] * nb
+        xd = self.x_dev if x_dev is None else x_dev
+        if x_dev is None:
+            with torch.cuda.stream(self.h2d):
+                for b in range(nb):
+                    lo, hi = b * bw, min((b + 1) * bw, self.ncols)
+                    if hi > lo:
+                        self.x_dev[lo:hi].copy_(x_host[lo:hi], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(self.h2d)
+                    ev_x.append(e)
+        waited = [x_dev is not None] * nb
         done_blocks = [0] * len(self.chunks)
         for (c, b) in self.order:
             if not waited[b]:
                 cur.wait_event(ev_x[b])
                 waited[b] = True
             if c < 0:                      # a whole-matrix launch of an early column block
-                self.full.spmv_part(b, self.x_dev, self.y_dev)
+                self.full.spmv_part(b, xd, self.y_dev)
                 for i in range(len(done_blocks)):
                     done_blocks[i] += 1
                 continue
@@ -348,9 +352,9 @@ class HostPipe:
                 if b == 0:
                     y_c.zero_()
             elif self.full is not None:
-                cb.spmv_part_accumulate(b, self.x_dev, y_c)
+                cb.spmv_part_accumulate(b, xd, y_c)
             else:
-                cb.spmv_part(b, self.x_dev, y_c)
+                cb.spmv_part(b, xd, y_c)
             done_blocks[c] += 1
             if done_blocks[c] == nb:       # chunk finished: its rows of y go home
                 e = torch.cuda.Event()

@@ -733,6 +733,14 @@ class csr_array(CompressedBase):
             if dist.world_size() == 1:
                 return spmv(self, x, out)
             x_dev = _x_to_device_dist(self, x)
+            if (self._colblock(blk) is not None and isinstance(out, torch.Tensor) and not out.is_cuda
+                    and out.is_contiguous() and out.dim() == 1 and out.numel() == blk.nrows
+                    and out.dtype == x_dev.dtype):
+                # column-blocked operand + host result: the last column block runs row chunk by row
+                # chunk and finished chunks of y travel home while the next ones are computed
+                self._hostpipe(blk).run(None, out, x_dev=x_dev)
+                torch.cuda.current_stream().synchronize()
+                return out
             y_dev = empty(blk.nrows, self.dtype)
             _spmv_block(self, blk, x_dev, y_dev)
             if out is None:

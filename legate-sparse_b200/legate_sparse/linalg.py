@@ -397,6 +397,32 @@ def cg_profile():
     return [(n, e0.elapsed_time(e1)) for (n, e0, e1) in _cg_profile]
 
 
+def _halo_ranges(blk, device):
+    """Per peer (rank order, self skipped): the slice [lo, hi) of MY row block that the peer's rows
+    touch — the [min col, max col] image of ITS rows (the reference's image(crd→x, MIN_MAX),
+    csr.py:591), clipped to my rows.  Collective (one all-gather of 2 integers).  None when every
+    peer needs (almost) everything."""
+    G = dist.world_size()
+    r0, r1 = blk.r0, blk.r1
+    cr = torch.tensor(list(blk.colrange()), dtype=torch.int64, device=device)
+    allcr = torch.empty(2 * G, dtype=torch.int64, device=device)
+    torch.distributed.all_gather_into_tensor(allcr, cr)
+    allcr = allcr.cpu().numpy().reshape(G, 2)
+    lo, hi = [], []
+    for g in range(G):
+        if g == dist.rank():
+            continue
+        a, b = max(int(allcr[g, 0]), r0), min(int(allcr[g, 1]) + 1, r1)
+        lo.append(max(a - r0, 0))
+        hi.append(max(b - r0, 0) if b > a else 0)
+        if b <= a:
+            lo[-1], hi[-1] = 1, 0          # empty: this peer never reads my block
+    sent = sum(max(h - l, 0) for l, h in zip(lo, hi))
+    if sent < (G - 1) * (r1 - r0):          # otherwise every peer needs everything
+        return (lo, hi)
+    return None
+
+
 class _CgState:
     """Buffers, halo ranges, exchange boards and CUDA graphs of the fused CG iteration for one
     (matrix block, dtype, world size, graph length).  Cached on the matrix (`A._cg_state`): a second
@@ -427,22 +453,7 @@ class _CgState:
             # halo exchange: peer g only needs the part of my p block inside the [min col, max col]
             # image of ITS rows (banded / stencil matrices: a few boundary rows instead of the block)
             if not isinstance(self.peer_ptrs, tuple) and os.environ.get("LEGATE_SPARSE_NO_HALO", "0") in ("0", ""):
-                cr = torch.tensor(list(blk.colrange()), dtype=torch.int64, device=self.p_full.device)
-                allcr = torch.empty(2 * G, dtype=torch.int64, device=self.p_full.device)
-                torch.distributed.all_gather_into_tensor(allcr, cr)
-                allcr = allcr.cpu().numpy().reshape(G, 2)
-                lo, hi = [], []
-                for g in range(G):
-                    if g == dist.rank():
-                        continue
-                    a, b = max(int(allcr[g, 0]), r0), min(int(allcr[g, 1]) + 1, r1)
-                    lo.append(max(a - r0, 0))
-                    hi.append(max(b - r0, 0) if b > a else 0)
-                    if b <= a:
-                        lo[-1], hi[-1] = 1, 0          # empty: this peer never reads my block
-                sent = sum(max(h - l, 0) for l, h in zip(lo, hi))
-                if sent < (G - 1) * (r1 - r0):          # otherwise every peer needs everything
-                    self.halo = (lo, hi)
+                self.halo = _halo_ranges(blk, self.p_full.device)
         else:
             self.p_full = D.zeros(n, dtype)
         self.p_loc = self.p_full[r0:r1]
@@ -646,14 +657,30 @@ def _gmres_sharded(A, b_dev, x, dtype, atol, restart, maxiter, callback, callbac
     hcol = torch.empty(restart, dtype=tdt, device=dev)
     hn = torch.empty(1, dtype=rdt, device=dev)
     e = np.zeros((restart + 1,), dtype=dtype)
-    z_full = torch.empty(n, dtype=tdt, device=dev)                # replicated operand of the SpMV
+    # replicated operand of the SpMV.  With peer memory: a symmetric buffer into which every rank
+    # copies only the slices its peers' rows touch (halo exchange over NVLink, like CG's p) + one
+    # barrier; otherwise (or when every peer needs everything) an NCCL all-gather of v_j.
+    zv = dist.symm_vector(n, tdt, "gmres_z")
+    halo = _halo_ranges(blk, dev) if (zv is not None and os.environ.get("LEGATE_SPARSE_NO_HALO", "0") in ("0", "")) else None
+    z_full = zv.t if zv is not None else torch.empty(n, dtype=tdt, device=dev)
+    peers = [g for g in range(G) if g != dist.rank()]
+    peer_bufs = [zv.h.get_buffer(g, (n,), tdt) for g in peers] if halo is not None else None
     u = torch.empty(nl, dtype=tdt, device=dev)
     x_loc = x[r0:r1].clone()
     b_loc = b_dev[r0:r1]
 
     def gather(v_loc):
         z_full[r0:r1].copy_(v_loc)
-        dist.allgather_into(z_full, bounds)
+        if halo is not None:
+            # the all-reduces of the previous step order every rank's SpMV (the reader of z_full)
+            # before these stores
+            for k, buf in enumerate(peer_bufs):
+                lo, hi = halo[0][k], halo[1][k]
+                if hi > lo:
+                    buf[r0 + lo : r0 + hi].copy_(v_loc[lo:hi])
+            zv.barrier()
+        else:
+            dist.allgather_into(z_full, bounds)
         return z_full
 
     def norm_all(sq_holder):

@@ -135,3 +135,73 @@ def test_config3_cg_solve_pinned_to_scipy_and_reference(N):
         want = pins[pre + who]
         assert np.linalg.norm(xs - want) / np.linalg.norm(want) < 1e-10, who
     assert abs(float(x.norm()) - float(pins[pre + "xnorm_scipy"])) < 1e-10 * float(pins[pre + "xnorm_scipy"])
+
+
+@pytest.mark.parametrize("n", [2_000_000, 8_000_000])
+def test_config5_powerlaw_full_size(n):
+    """BASELINE config 5 at full size (and at the 2M-row size whose power-law leg once ended in an
+    illegal memory access in round 1): power-law row degrees clipped to [1, 10000] with one 10000-entry
+    row, uniform columns.  Properties: bit-reproducible, linear, the long-row pass on and off give the
+    same y, sampled rows (short, long, the longest) equal the oracle's C loop to 1e-10."""
+    import torch
+
+    import bench
+    import legate_sparse as sparse
+    from oracle import oracle
+
+    dev = torch.device("cuda")
+    vals, cols, ptr, x, nnz = bench.powerlaw_matrix(n, dev)
+    deg = ptr[1:] - ptr[:-1]
+    assert int(deg.max()) == 10000 and int(deg.min()) >= 1
+    A = sparse.csr_array((vals, cols, ptr), shape=(n, n))
+    y = A @ x
+    assert torch.equal(y, A @ x)                         # no atomics on the path
+    assert torch.equal(A @ (2.0 * x), 2.0 * y)           # scaling by 2 is exact
+    os.environ["B2S_SPMV_LONGROWS"] = "0"
+    try:
+        B = sparse.csr_array((vals, cols, ptr), shape=(n, n))
+        y0 = B @ x
+    finally:
+        os.environ.pop("B2S_SPMV_LONGROWS")
+    assert float((y0 - y).abs().max() / y.abs().max()) < 1e-13
+    rows = torch.cat([torch.linspace(0, n - 1, 400, device=dev).long(), torch.topk(deg, 20).indices,
+                      torch.tensor([n // 3, 0, n - 1], device=dev)]).unique().tolist()
+    xs = x.cpu().numpy()
+    for r in rows:
+        a, b = int(ptr[r]), int(ptr[r + 1])
+        ref = oracle.spmv(np.array([0, b - a]), cols[a:b].cpu().numpy(), vals[a:b].cpu().numpy(), xs)[0]
+        assert abs(float(y[r]) - ref) <= 1e-10 * max(abs(ref), 1e-300), r
+
+
+def test_config4_rmat16_sampled_rows_vs_oracle():
+    """BASELINE config 4's generator at scale 16 (the largest the CPU oracle checks in seconds per
+    row): C = A @ A structure bit-exact and values to 1e-10 on sampled rows incl. the heaviest ones
+    (dense-accumulator class) against the oracle's Gustavson (spgemm_csr_csr_csr.cc:62-87,134-158)."""
+    import torch
+
+    import bench
+    import legate_sparse as sparse
+    from side_bench import rmat_device
+
+    dev = torch.device("cuda")
+    data, idx, ptr, n = rmat_device(16, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    data = torch.rand(data.numel(), dtype=torch.float64, device=dev, generator=g) + 0.5    # not all ones
+    A = sparse.csr_array((data, idx, ptr), shape=(n, n))
+    C = A @ A
+    blk = C._block()
+    assert int(blk.indptr[-1]) == C.nnz
+    heavy = torch.topk(ptr[1:] - ptr[:-1], 6).indices.tolist()
+    ip, ix, dv = ptr.cpu().numpy(), idx.cpu().numpy().astype(np.int64), data.cpu().numpy()
+    from oracle import oracle
+
+    rows = sorted(set(heavy + torch.linspace(0, n - 1, 40).long().tolist()))
+    for r in rows:
+        a_ptr = np.array([0, ip[r + 1] - ip[r]], dtype=np.int64)
+        cp, ci, cv = oracle.spgemm(a_ptr, ix[ip[r]:ip[r + 1]], dv[ip[r]:ip[r + 1]], ip, ix, dv, n)
+        order = np.argsort(ci, kind="stable")
+        lo, hi = int(blk.indptr[r]), int(blk.indptr[r + 1])
+        assert np.array_equal(blk.indices[lo:hi].cpu().numpy().astype(np.int64), ci[order]), r
+        got = blk.data[lo:hi].cpu().numpy()
+        assert np.all(np.abs(got - cv[order]) <= 1e-10 * np.abs(cv[order])), r

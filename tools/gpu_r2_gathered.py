@@ -31,6 +31,9 @@ res = {"sharded": timeit(lambda: A.dot_local(x, out=y_loc))}
 res["gathered_out"] = timeit(lambda: A.dot(x, out=y_full))
 ref = y_full.clone()
 res["gathered_clone"] = timeit(lambda: A.dot(x))
+y_sym = dist.replicated_empty(n, torch.float64)
+res["gathered_symm_out"] = timeit(lambda: A.dot(x, out=y_sym))
+assert torch.equal(y_sym, ref)
 # barrier cost alone
 sv = dist.symm_vector(n, torch.float64, "spmv_y0")
 if sv is not None:
