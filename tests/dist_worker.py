@@ -46,6 +46,13 @@ def main():
     assert Ab._block().colblock not in (None, False)
     assert relerr(yb, S @ x) < 1e-12
     assert relerr(Ab @ (2.0 * x), 2.0 * (S @ x)) < 1e-12   # second call: buffers reused after the barrier
+    # host vectors + column-blocked operand: chunked last block, y chunks copied back as they finish
+    bb = Ab._block()
+    yb_host = torch.empty(bb.nrows, dtype=torch.float64).pin_memory()
+    for s_ in (1.0, 3.0):
+        Ab.dot_local(torch.from_numpy(s_ * x).pin_memory(), out=yb_host)
+        assert relerr(yb_host.numpy(), s_ * (S @ x)[bb.r0 : bb.r1]) < 1e-12
+    assert bb.hostpipe is not None
     os.environ.pop("B2S_SPMV_COLBLOCK")
     # nnz-balanced partition on a power-law matrix
     d, c, p = gen.powerlaw_csr(8000, 8000, max_row=4000, seed=7)

@@ -218,3 +218,37 @@ def test_colblock_suggested_for_wide_random_matrix():
     want = sp.csr_matrix((vals, cols, indptr), shape=(m, n)) @ x
     assert np.allclose(y.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
     lib.b2s_csr_colblock_destroy(h)
+
+
+@pytest.mark.parametrize("chunks", ["1", "3", "16"])
+def test_host_vector_pipeline_2d_blocks(monkeypatch, chunks):
+    """A.dot(x_host[, out=y_host]) with a column-blocked operand runs the 2-D pipeline
+    (_device.HostPipe: early column blocks whole, the last one row chunk by row chunk, y chunks copied
+    back as they finish): numpy / pinned / unpinned vectors, empty row ranges, any chunk count."""
+    import torch
+
+    import legate_sparse as sparse
+
+    monkeypatch.setenv("B2S_SPMV_COLBLOCK", "3")
+    monkeypatch.setenv("LEGATE_SPARSE_HOSTPIPE_CHUNKS", chunks)
+    rng = np.random.default_rng(21)
+    S = sp.random(6001, 9000, density=0.003, format="lil", random_state=4, dtype=np.float64)
+    S[1000:2500, :] = 0          # a stretch of empty rows (a whole chunk at 16 chunks)
+    S = S.tocsr()
+    S.sort_indices()
+    A = sparse.csr_array((S.data, S.indices, S.indptr), shape=S.shape)
+    x = rng.standard_normal(9000)
+    want = S @ x
+    y = A @ x                                            # numpy in, numpy out
+    assert isinstance(y, np.ndarray) and np.allclose(y, want, rtol=1e-12, atol=1e-12)
+    assert A._block().hostpipe is not None
+    out = np.full(6001, 7.0)
+    assert A.dot(x, out=out) is out and np.allclose(out, want, rtol=1e-12, atol=1e-12)
+    xh = torch.from_numpy(x).pin_memory()
+    yh = torch.empty(6001, dtype=torch.float64).pin_memory()
+    for s_ in (1.0, -2.0):                               # buffers of the pipeline are reused call after call
+        A.dot(s_ * xh, out=yh)
+        assert np.allclose(yh.numpy(), s_ * want, rtol=1e-12, atol=1e-12)
+    # the device-vector path of the same matrix is untouched by the pipeline's operands
+    yd = A @ torch.from_numpy(x).cuda()
+    assert np.allclose(yd.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
