@@ -233,6 +233,17 @@ int64_t b2s_board_bytes(void);
 int b2s_allreduce_board(b2s_dtype vt, void* inout, void* const* boards, int rank, int nranks,
                         int channel, void* seq_counters, void* cur_out, void* prev_out, void* err,
                         b2s_stream_t stream);
+/* The same exchange folded into the final reduction of the producing kernel (one launch less per
+ * exchange): b2s_cg_update whose r.r, and b2s_spmv_csr_dot whose w.y, come out summed over the ranks. */
+int b2s_cg_update_allreduce(b2s_dtype vt, int64_t n, void* x, void* r, const void* p, const void* q,
+                            const void* rho, const void* pq, void* rr_out, void* partials,
+                            void* const* boards, int rank, int nranks, int channel, void* seq_counters,
+                            void* cur_out, void* prev_out, void* err, b2s_stream_t stream);
+int b2s_spmv_csr_dot_allreduce(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                               const int64_t* indptr, const void* indices, const void* data,
+                               const void* x, void* y, const void* w, const b2s_spmv_plan* plan,
+                               void* dot_out, void* const* boards, int rank, int nranks, int channel,
+                               void* seq_counters, void* err, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * CSR x CSR SpGEMM  C = A B.   replaces SpGEMMCSRxCSRxCSRGPU

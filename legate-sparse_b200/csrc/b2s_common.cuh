@@ -389,10 +389,20 @@ __host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { ret
 // b2s_spgemm.cu: in-place inclusive scan of v[0..n), first[0] = 0; blocksum = ceil(n/1024)+1 int64 scratch
 int scan_inclusive_i64(int64_t n, int64_t* v, int64_t* first, int64_t* blocksum, cudaStream_t st);
 // b2s_spmv.cu: the one SpMV entry (accumulate != 0: y += A x, pipe kernel only)
+// raw (type-erased) arguments of a cross-rank board exchange folded into a reduction (b2s_board.cuh)
+struct BoardRaw {
+  void* const* boards;
+  int rank, nranks, channel;
+  void* seq_counters;
+  void* cur_out;
+  void* prev_out;
+  void* err;
+};
 int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
                const int64_t* indptr, const void* indices, const void* data, const void* x, void* y,
                const b2s_spmv_plan* plan, int variant, void* dot_out, void* partials, const void* w,
-               void* const* y_peers, int npeers, int accumulate, b2s_stream_t stream);
+               void* const* y_peers, int npeers, int accumulate, b2s_stream_t stream,
+               const BoardRaw* board = nullptr);
 int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* indptr,
                      const void* indices, void* workspace, int64_t workspace_bytes, b2s_stream_t stream,
                      int64_t force_tile, b2s_spmv_plan** out_plan);

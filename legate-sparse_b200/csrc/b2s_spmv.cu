@@ -17,6 +17,7 @@
 //       No floating-point atomics anywhere.
 //   * spmv_rowvec_kernel — plan-free LANES-per-row kernel (small / one-shot matrices).
 #include "b2s_common.cuh"
+#include "b2s_board.cuh"
 
 namespace b2s {
 
@@ -296,17 +297,21 @@ __global__ void spmv_fixup_kernel(int64_t ntiles, int64_t tile_nnz,
 
 // final deterministic reduction of per-tile partials → out[0]
 template <typename V>
-__global__ void reduce_partials_kernel(int64_t n, const V* __restrict__ partials, V* __restrict__ out) {
+__global__ void reduce_partials_kernel(int64_t n, const V* __restrict__ partials, V* __restrict__ out,
+                                       const BoardArgs<V> bx) {
   __shared__ V sh[32];
+  __shared__ V xvals[kBoardRanks];
   V s = zero_of<V>();
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = vadd(s, partials[i]);
   for (int o = 16; o > 0; o >>= 1) s = vadd(s, vshfl_xor(s, o));
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     V tot = sh[0];
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) tot = vadd(tot, sh[i]);
-    out[0] = tot;
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) tot = vadd(tot, sh[i]);   // same order in every lane
+    // several ranks: the sum over the ranks is taken right here (board exchange, b2s_board.cuh)
+    if (bx.nranks > 1) tot = board_exchange_warp<V>(tot, bx, xvals);
+    if (threadIdx.x == 0) out[0] = tot;
   }
 }
 
@@ -498,7 +503,7 @@ static int launch_tile_ipt(const PlanHeader* P, const int64_t* indptr, const I* 
 template <typename V, typename I, bool DOT>
 static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                     const V* x, V* y, V* dot_out, V* dot_partials, const V* w, int mode,
-                    const PeerOut<V>& peers, int accumulate, cudaStream_t st) {
+                    const PeerOut<V>& peers, int accumulate, const BoardRaw* board, cudaStream_t st) {
   int rc;
   int64_t npartials = P->ntiles;
   if (mode == 1) {
@@ -520,7 +525,13 @@ static int run_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, c
     B2S_CHECK_LAUNCH();
   }
   if (DOT) {
-    reduce_partials_kernel<V><<<1, 1024, 0, st>>>(npartials, dot_partials, dot_out);
+    BoardArgs<V> bx{};
+    if (board) {
+      int rcb = make_board_args<V>(board->boards, board->rank, board->nranks, board->channel, board->seq_counters,
+                                   board->cur_out, board->prev_out, board->err, &bx);
+      if (rcb) return rcb;
+    }
+    reduce_partials_kernel<V><<<1, 1024, 0, st>>>(npartials, dot_partials, dot_out, bx);
     B2S_CHECK_LAUNCH();
   }
   return B2S_OK;
@@ -561,7 +572,7 @@ template <typename V, typename I>
 static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* indptr, const I* cols,
                       const V* vals, const V* x, V* y, const PlanHeader* P, int variant, V* dot_out,
                       V* dot_partials, const V* w, const PeerOut<V>& peers, int accumulate,
-                      cudaStream_t st) {
+                      const BoardRaw* board, cudaStream_t st) {
   const bool want_dot = dot_out != nullptr;
   if (nrows == 0) {
     if (want_dot) { fill_zero_kernel<V><<<1, 32, 0, st>>>(1, dot_out); B2S_CHECK_LAUNCH(); }
@@ -604,8 +615,8 @@ static int spmv_typed(int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* 
       set_error("y += A x needs the pipe kernel (16-byte aligned arrays, 1024/2048-nnz plan)");
       return B2S_ERR_UNSUPPORTED;
     }
-    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, peers, accumulate, st);
-    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, peers, accumulate, st);
+    if (want_dot) return run_tile<V, I, true>(P, indptr, cols, vals, x, y, dot_out, dot_partials, w, mode, peers, accumulate, board, st);
+    return run_tile<V, I, false>(P, indptr, cols, vals, x, y, nullptr, nullptr, nullptr, mode, peers, accumulate, nullptr, st);
   }
   if (peers.n != 0 || accumulate) {
     set_error("peer broadcast / accumulate need a plan");
@@ -726,7 +737,8 @@ namespace b2s {
 int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
                const int64_t* indptr, const void* indices, const void* data, const void* x,
                void* y, const b2s_spmv_plan* plan, int variant, void* dot_out, void* partials,
-               const void* w, void* const* y_peers, int npeers, int accumulate, b2s_stream_t stream) {
+               const void* w, void* const* y_peers, int npeers, int accumulate, b2s_stream_t stream,
+               const BoardRaw* board) {
   B2S_REQUIRE(npeers >= -1 && npeers <= kMaxPeers, "npeers must be in [-1,7]");
   B2S_REQUIRE(npeers == 0 || y_peers != nullptr, "y_peers is null");
   B2S_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative size");
@@ -742,7 +754,7 @@ int spmv_entry(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t
     B2S_DISPATCH_IT(it, I,
       return spmv_typed<V, I>(nrows, ncols, nnz, indptr, (const I*)indices, (const V*)data,
                               (const V*)x, (V*)y, plan, variant, (V*)dot_out, (V*)partials, (const V*)w,
-                              peers, accumulate, st));
+                              peers, accumulate, board, st));
   });
   return B2S_ERR_ARG;
 }
@@ -764,6 +776,22 @@ extern "C" int b2s_spmv_csr_bcast(b2s_dtype vt, b2s_itype it, int64_t nrows, int
   B2S_REQUIRE(plan != nullptr, "broadcast SpMV needs a plan");
   return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO, nullptr,
                     nullptr, nullptr, y_peers, npeers, 0, stream);
+}
+
+// b2s_spmv_csr_dot whose w.y is summed over the ranks inside the final reduction kernel (board
+// exchange, see b2s_allreduce_board): dot_out[0] = sum over ranks of this rank's sum_r w[r] y[r].
+extern "C" int b2s_spmv_csr_dot_allreduce(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
+                                          const int64_t* indptr, const void* indices, const void* data,
+                                          const void* x, void* y, const void* w, const b2s_spmv_plan* plan,
+                                          void* dot_out, void* const* boards, int rank, int nranks, int channel,
+                                          void* seq_counters, void* err, b2s_stream_t stream) {
+  B2S_REQUIRE(dot_out != nullptr, "dot_out null");
+  B2S_REQUIRE(nrows == 0 || w != nullptr, "w null");
+  B2S_REQUIRE(plan != nullptr, "fused dot needs a plan");
+  B2S_REQUIRE(boards != nullptr && nranks >= 2, "b2s_spmv_csr_dot_allreduce needs boards of >= 2 ranks");
+  BoardRaw br{boards, rank, nranks, channel, seq_counters, nullptr, nullptr, err};
+  return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO,
+                    dot_out, plan->dotp, w, nullptr, 0, 0, stream, &br);
 }
 
 extern "C" int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,

@@ -5,6 +5,7 @@
 //   AXPBY  src/sparse/linalg/axpby.cu:25-47, axpby.cc:34-44 (val = a[0]/b[0], optional negate)
 //   dots / norms are cupynumeric calls in legate_sparse/linalg.py:482,510,520,529.
 #include "b2s_common.cuh"
+#include "b2s_board.cuh"
 
 namespace b2s {
 
@@ -84,6 +85,35 @@ __device__ __forceinline__ void finish_reduce(A local, A* partials, unsigned* co
   }
 }
 
+// the same with the cross-rank exchange folded into the last CTA's epilogue (bx.nranks > 1)
+template <typename A>
+__device__ __forceinline__ void finish_reduce_exchange(A local, A* partials, unsigned* counter, A* out, const BoardArgs<A>& bx) {
+  __shared__ A wsum[kVecThreads / 32];
+  __shared__ A xvals[kBoardRanks];
+  __shared__ bool is_last;
+  A s = local;
+  for (int o = 16; o > 0; o >>= 1) s = vadd(s, vshfl_xor(s, o));
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    A tot = wsum[0];
+    for (int i = 1; i < kVecThreads / 32; ++i) tot = vadd(tot, wsum[i]);
+    partials[blockIdx.x] = tot;
+    __threadfence();
+    unsigned prev = atomicInc(counter, gridDim.x - 1);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    A acc = zero_of<A>();
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) acc = vadd(acc, ld_cg(&partials[i]));
+    for (int o = 16; o > 0; o >>= 1) acc = vadd(acc, vshfl_xor(acc, o));   // every lane holds the local sum
+    if (bx.nranks > 1) acc = board_exchange_warp<A>(acc, bx, xvals);
+    if (threadIdx.x == 0) out[0] = acc;
+  }
+}
+
 template <typename V, bool VEC, bool CONJ>
 __global__ void __launch_bounds__(kVecThreads)
 dot_kernel(int64_t n, const V* __restrict__ x, const V* __restrict__ y, V* partials,
@@ -137,7 +167,7 @@ template <typename V, bool VEC>
 __global__ void __launch_bounds__(kVecThreads)
 cg_update_kernel(int64_t n, V* __restrict__ x, V* __restrict__ r, const V* __restrict__ p,
                  const V* __restrict__ q, const V* __restrict__ rho, const V* __restrict__ pq,
-                 V* partials, unsigned* counter, V* rr_out) {
+                 V* partials, unsigned* counter, V* rr_out, const BoardArgs<V> bx) {
   const V alpha = vdiv(rho[0], pq[0]);
   const V nalpha = vneg(alpha);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -175,7 +205,7 @@ cg_update_kernel(int64_t n, V* __restrict__ x, V* __restrict__ r, const V* __res
       acc = vfma(rv, rv, acc);
     }
   }
-  finish_reduce(acc, partials, counter, rr_out, [] __device__(V v) { return v; });
+  finish_reduce_exchange<V>(acc, partials, counter, rr_out, bx);
 }
 
 // p = r + (rho/rho1) p ; rho1 == 0 → p = r
@@ -294,22 +324,47 @@ extern "C" int b2s_nrm2(b2s_dtype vt, int64_t n, const void* x, void* out, void*
   return B2S_OK;
 }
 
-extern "C" int b2s_cg_update(b2s_dtype vt, int64_t n, void* x, void* r, const void* p, const void* q,
-                             const void* rho, const void* pq, void* rr_out, void* partials,
-                             b2s_stream_t stream) {
+static int cg_update_impl(b2s_dtype vt, int64_t n, void* x, void* r, const void* p, const void* q,
+                          const void* rho, const void* pq, void* rr_out, void* partials, void* const* boards,
+                          int rank, int nranks, int channel, void* seq_counters, void* cur_out, void* prev_out,
+                          void* err, b2s_stream_t stream) {
   B2S_REQUIRE(n >= 0, "negative n");
   B2S_REQUIRE(rr_out && partials && rho && pq, "null scalar/workspace");
   B2S_REQUIRE(n == 0 || (x && r && p && q), "null vectors");
   cudaStream_t st = (cudaStream_t)stream;
   RedWs w = carve(partials);
   B2S_DISPATCH_VT(vt, V, {
+    BoardArgs<V> bx;
+    int rc = make_board_args<V>(boards, rank, nranks, channel, seq_counters, cur_out, prev_out, err, &bx);
+    if (rc) return rc;
     bool vec = aligned16(x) && aligned16(r) && aligned16(p) && aligned16(q);
-    int64_t grid = vec_grid(ceil_div(n, (int64_t)Pack<V>::N));
-    if (vec) cg_update_kernel<V, true><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)x, (V*)r, (const V*)p, (const V*)q, (const V*)rho, (const V*)pq, (V*)w.partials, w.counter, (V*)rr_out);
-    else     cg_update_kernel<V, false><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)x, (V*)r, (const V*)p, (const V*)q, (const V*)rho, (const V*)pq, (V*)w.partials, w.counter, (V*)rr_out);
+    int64_t grid = vec_grid(ceil_div(n > 0 ? n : 1, (int64_t)Pack<V>::N));
+    if (vec) cg_update_kernel<V, true><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)x, (V*)r, (const V*)p, (const V*)q, (const V*)rho, (const V*)pq, (V*)w.partials, w.counter, (V*)rr_out, bx);
+    else     cg_update_kernel<V, false><<<(unsigned)grid, kVecThreads, 0, st>>>(n, (V*)x, (V*)r, (const V*)p, (const V*)q, (const V*)rho, (const V*)pq, (V*)w.partials, w.counter, (V*)rr_out, bx);
     B2S_CHECK_LAUNCH();
   });
   return B2S_OK;
+}
+
+extern "C" int b2s_cg_update(b2s_dtype vt, int64_t n, void* x, void* r, const void* p, const void* q,
+                             const void* rho, const void* pq, void* rr_out, void* partials,
+                             b2s_stream_t stream) {
+  return cg_update_impl(vt, n, x, r, p, q, rho, pq, rr_out, partials, nullptr, 0, 0, 0, nullptr, nullptr, nullptr,
+                        nullptr, stream);
+}
+
+// cg_update whose r.r is summed over the ranks inside the kernel's final reduction (board exchange,
+// see b2s_allreduce_board): rr_out[0] = sum over ranks; optionally prev_out[0] = cur_out[0],
+// cur_out[0] = sum (CG: rho1 <- rho, rho <- r.r).
+extern "C" int b2s_cg_update_allreduce(b2s_dtype vt, int64_t n, void* x, void* r, const void* p, const void* q,
+                                       const void* rho, const void* pq, void* rr_out, void* partials,
+                                       void* const* boards, int rank, int nranks, int channel,
+                                       void* seq_counters, void* cur_out, void* prev_out, void* err,
+                                       b2s_stream_t stream) {
+  B2S_REQUIRE(boards != nullptr && nranks >= 2, "b2s_cg_update_allreduce needs boards of >= 2 ranks");
+  B2S_REQUIRE((prev_out == nullptr) || (cur_out != nullptr), "prev_out needs cur_out");
+  return cg_update_impl(vt, n, x, r, p, q, rho, pq, rr_out, partials, boards, rank, nranks, channel, seq_counters,
+                        cur_out, prev_out, err, stream);
 }
 
 static int cg_pupdate_impl(b2s_dtype vt, int64_t n, void* p, const void* r, const void* rho,
@@ -368,84 +423,14 @@ extern "C" int b2s_cg_pupdate_halo(b2s_dtype vt, int64_t n, void* p, const void*
 // (reference linalg.py:519-526 gets the same values from Legate future reductions).
 namespace b2s {
 
-constexpr int kBoardChannels = 4;
-constexpr int kBoardRanks    = kMaxPeers + 1;
-struct alignas(32) BoardSlot {
-  unsigned char value[16];      // packed form (values <= 8 bytes): bytes 0..7 payload, 8..15 sequence number
-  unsigned long long seq;       // c128 form: 16-byte value above, sequence number here
-  unsigned long long pad;
-};
-struct BoardPtrs { BoardSlot* b[kBoardRanks]; };
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// 16-byte slot accesses: {payload, seq} travel in ONE store / load, so no fence is needed between
-// the value and its flag (a 16-byte aligned vector access is a single transaction on NVLink and L2)
-__device__ __forceinline__ void st_slot16(void* p, unsigned long long payload, unsigned long long seq) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(payload), "l"(seq) : "memory");
-}
-__device__ __forceinline__ void ld_slot16(const void* p, unsigned long long* payload, unsigned long long* seq) {
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(*payload), "=l"(*seq) : "l"(p) : "memory");
-}
-
-// inout[0]: this rank's partial on entry, the global sum on exit.  prev_out (optional):
-// prev_out[0] = cur_out[0]; cur_out[0] = sum  (CG: rho1 <- rho, rho <- rr) — saves two copy kernels.
-// Values of up to 8 bytes (f32, f64, c64) are exchanged as {value, seq} pairs in one 16-byte store;
-// c128 uses the value + release/acquire flag form.
+// inout[0]: this rank's partial on entry, the global sum on exit (stand-alone form; cg_update and
+// the SpMV's fused dot fold the same exchange into their final reduction).
 template <typename V>
 __global__ void __launch_bounds__(32)
-allreduce_board_kernel(V* __restrict__ inout, const BoardPtrs boards, int rank, int nranks, int channel,
-                       unsigned long long* __restrict__ seq_counters, V* __restrict__ cur_out,
-                       V* __restrict__ prev_out, int* __restrict__ err) {
+allreduce_board_kernel(V* __restrict__ inout, const BoardArgs<V> bx) {
   __shared__ V vals[kBoardRanks];
-  const int t = threadIdx.x;
-  const unsigned long long seq = seq_counters[channel] + 1ull;
-  const int slot_base = (channel * 2 + (int)(seq & 1ull)) * kBoardRanks;
-  if (t < nranks) {
-    const V mine = inout[0];
-    BoardSlot* dst = boards.b[t] + slot_base + rank;          // my slot on rank t's board
-    BoardSlot* src = boards.b[rank] + slot_base + t;           // rank t's slot on my board
-    const long long t0 = clock64();
-    bool ok = true;
-    if constexpr (sizeof(V) <= 8) {
-      unsigned long long payload = 0;
-      memcpy(&payload, &mine, sizeof(V));
-      st_slot16(dst, payload, seq);                            // slot bytes 0..15 = {payload, seq}
-      unsigned long long got = 0, gseq = 0;
-      while (true) {
-        ld_slot16(src, &got, &gseq);
-        if (gseq == seq) break;
-        if (clock64() - t0 > (1ll << 34)) { ok = false; break; }   // ~8 s: a peer died — do not hang the GPU
-      }
-      V v;
-      memcpy(&v, &got, sizeof(V));
-      vals[t] = v;
-    } else {
-      *reinterpret_cast<V*>(dst->value) = mine;
-      st_release_sys(&dst->seq, seq);                           // value first, then the flag
-      while (ld_acquire_sys(&src->seq) != seq) {
-        if (clock64() - t0 > (1ll << 34)) { ok = false; break; }
-      }
-      vals[t] = *reinterpret_cast<const V*>(src->value);        // ordered after the acquire load above
-    }
-    if (!ok && err) atomicExch(err, 1);
-  }
-  __syncwarp();
-  if (t == 0) {
-    V tot = vals[0];
-    for (int g = 1; g < nranks; ++g) tot = vadd(tot, vals[g]);
-    inout[0] = tot;
-    if (prev_out) prev_out[0] = cur_out[0];
-    if (cur_out) cur_out[0] = tot;
-    seq_counters[channel] = seq;
-  }
+  const V tot = board_exchange_warp<V>(inout[0], bx, vals);
+  if (threadIdx.x == 0) inout[0] = tot;
 }
 
 }  // namespace b2s
@@ -465,16 +450,20 @@ extern "C" int b2s_allreduce_board(b2s_dtype vt, void* inout, void* const* board
   B2S_REQUIRE(channel >= 0 && channel < kBoardChannels, "bad channel");
   B2S_REQUIRE(inout && boards && seq_counters, "null pointer");
   B2S_REQUIRE((prev_out == nullptr) || (cur_out != nullptr), "prev_out needs cur_out");
-  BoardPtrs bp{};
-  for (int g = 0; g < nranks; ++g) {
-    B2S_REQUIRE(boards[g] != nullptr, "null board pointer");
-    bp.b[g] = reinterpret_cast<BoardSlot*>(boards[g]);
-  }
   cudaStream_t st = (cudaStream_t)stream;
   B2S_DISPATCH_VT(vt, V, {
-    allreduce_board_kernel<V><<<1, 32, 0, st>>>((V*)inout, bp, rank, nranks, channel,
-                                                (unsigned long long*)seq_counters, (V*)cur_out, (V*)prev_out,
-                                                (int*)err);
+    BoardArgs<V> bx;
+    // nranks == 1 still goes through the board (a rank exchanging with itself): same code path everywhere
+    BoardArgs<V> tmp{};
+    for (int g = 0; g < nranks; ++g) {
+      B2S_REQUIRE(boards[g] != nullptr, "null board pointer");
+      tmp.boards.b[g] = reinterpret_cast<BoardSlot*>(boards[g]);
+    }
+    tmp.rank = rank; tmp.nranks = nranks; tmp.channel = channel;
+    tmp.seq_counters = reinterpret_cast<unsigned long long*>(seq_counters);
+    tmp.cur_out = (V*)cur_out; tmp.prev_out = (V*)prev_out; tmp.err = (int*)err;
+    bx = tmp;
+    allreduce_board_kernel<V><<<1, 32, 0, st>>>((V*)inout, bx);
     B2S_CHECK_LAUNCH();
   });
   return B2S_OK;

@@ -428,7 +428,15 @@ def cg_pupdate_halo(p, r, rho, rho1, peer_ptrs, lo, hi):
     )
 
 
-def spmv_dot(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, w, plan, dot_out):
+def spmv_dot(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, w, plan, dot_out, board=None, channel=0):
+    if board is not None:   # w.y summed over the ranks inside the final reduction kernel
+        N.check(
+            N.load().b2s_spmv_csr_dot_allreduce(
+                vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), ptr(w),
+                plan.handle, ptr(dot_out), ctypes.cast(board.arr, c_void_p), board.rank, board.nranks, int(channel),
+                ptr(board.seq), ptr(board.err), stream_ptr()),
+            "spmv_csr_dot_allreduce")
+        return
     N.check(
         N.load().b2s_spmv_csr_dot(
             vt, it, nrows, ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), ptr(w),
@@ -504,8 +512,16 @@ def vscale_inv(x, s, out):
     return out
 
 
-def cg_update(x, r, p, q, rho, pq, rr_out, ws=None):
+def cg_update(x, r, p, q, rho, pq, rr_out, ws=None, board=None, channel=0, cur_out=None, prev_out=None):
     dt = np_dtype_of(x)
+    if board is not None:   # r.r summed over the ranks inside the kernel's final reduction
+        N.check(
+            N.load().b2s_cg_update_allreduce(
+                vt_enum(dt), x.numel(), ptr(x), ptr(r), ptr(p), ptr(q), ptr(rho), ptr(pq), ptr(rr_out),
+                ptr(ws if ws is not None else reduce_ws()), ctypes.cast(board.arr, c_void_p), board.rank,
+                board.nranks, int(channel), ptr(board.seq), ptr(cur_out), ptr(prev_out), ptr(board.err), stream_ptr()),
+            "cg_update_allreduce")
+        return
     N.check(
         N.load().b2s_cg_update(vt_enum(dt), x.numel(), ptr(x), ptr(r), ptr(p), ptr(q), ptr(rho), ptr(pq),
                                ptr(rr_out), ptr(ws if ws is not None else reduce_ws()), stream_ptr()),

@@ -62,6 +62,8 @@ SIGNATURES = {
     "b2s_cg_pupdate_halo": (c_int, [c_int, _I64, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "b2s_board_bytes": (_I64, []),
     "b2s_allreduce_board": (c_int, [c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "b2s_cg_update_allreduce": (c_int, [c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "b2s_spmv_csr_dot_allreduce": (c_int, [c_int, c_int, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "b2s_spgemm_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "b2s_spgemm_symbolic": (
         c_int,

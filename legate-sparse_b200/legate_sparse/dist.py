@@ -277,6 +277,7 @@ class ScalarBoard:
         self.arr = (ctypes.c_void_p * len(self.ptrs))(*[ctypes.c_void_p(q) for q in self.ptrs])
         self.seq = torch.zeros(8, dtype=torch.int64, device=dev)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.rank, self.nranks = rank(), world_size()
         torch.cuda.synchronize()
         self.h.barrier(channel=0)        # every board is zeroed before anyone writes a slot
         torch.cuda.synchronize()

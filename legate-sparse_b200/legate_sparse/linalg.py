@@ -491,16 +491,24 @@ class _CgState:
             D.cg_pupdate(self.p_loc, self.r, self.rho, self.rho1)
             if G > 1:
                 dist.allgather_into(self.p_full, self.bounds)
+        fuse = self.board is not None and os.environ.get("LEGATE_SPARSE_CG_NO_FUSED_EXCHANGE", "0") in ("0", "")
         if self.plan is not None:
+            # several ranks: the p.q partials are exchanged inside the dot's final reduction kernel
             D.spmv_dot(self.vt, blk.itype, blk.nrows, self.ncols, blk.nnz, blk.indptr, blk.indices, blk.data,
-                       self.p_full, self.q, self.p_loc, self.plan, self.pq)
+                       self.p_full, self.q, self.p_loc, self.plan, self.pq,
+                       board=self.board if fuse else None, channel=1)
         else:  # empty block
             self.q.zero_()
             self.pq.zero_()
-        if self.board is not None:
+        if self.board is not None and (not fuse or self.plan is None):
             self.board.allreduce(self.pq, 1)
-        else:
+        elif self.board is None:
             dist.allreduce_sum_(self.pq)
+        if fuse:
+            # ... and the r.r partials inside cg_update's last CTA (rho1 <- rho ; rho <- sum(rr) there too)
+            D.cg_update(self.x_loc, self.r, self.p_loc, self.q, self.rho, self.pq, self.rr, ws=self.red_ws,
+                        board=self.board, channel=2, cur_out=self.rho, prev_out=self.rho1)
+            return
         D.cg_update(self.x_loc, self.r, self.p_loc, self.q, self.rho, self.pq, self.rr, ws=self.red_ws)
         if self.board is not None:
             self.board.allreduce(self.rr, 2, cur_out=self.rho, prev_out=self.rho1)   # rho1 <- rho ; rho <- sum(rr)
