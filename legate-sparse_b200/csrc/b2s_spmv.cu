@@ -804,3 +804,14 @@ extern "C" int b2s_spmv_csr_dot(b2s_dtype vt, b2s_itype it, int64_t nrows, int64
   return spmv_entry(vt, it, nrows, ncols, nnz, indptr, indices, data, x, y, plan, B2S_SPMV_AUTO,
                     dot_out, plan->dotp, w, nullptr, 0, 0, stream);
 }
+
+#ifdef B2S_PIPE_TIMING
+// debug builds only: read and clear the phase cycle counters of the pipe kernel
+extern "C" int b2s_debug_pipe_phases(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, b2s::g_pipe_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(b2s::g_pipe_phase, z, sizeof z);
+  return 0;
+}
+#endif

@@ -26,6 +26,14 @@
 
 namespace b2s {
 
+#ifdef B2S_PIPE_TIMING
+// phase cycle counters of consumer group 0 / thread 0 of CTA 0 (debug builds only, tools/gpu_r2_timing.sh)
+__device__ unsigned long long g_pipe_phase[16];
+#define B2S_T(k) do { if (blockIdx.x == 0 && tid == 0) { const long long _n = clock64(); g_pipe_phase[k] += (unsigned long long)(_n - _tprev); _tprev = _n; } } while (0)
+#else
+#define B2S_T(k) do { } while (0)
+#endif
+
 constexpr int kPipeConsumers = 256;
 constexpr int kPipeThreads   = kPipeConsumers + 32;
 constexpr int kPipeWinCap    = 1024;  // x-window capacity per stage (elements)
@@ -88,7 +96,7 @@ template <typename I, int C> struct alignas((sizeof(I) * C) < 16 ? (sizeof(I) * 
 // stalls its whole group at the next barrier: 41 % barrier stalls on BASELINE config 5) but
 // deferred to a second pass where each gets a full warp.
 template <typename V, typename I, int TILE, int STAGES, bool WINDOW, bool DOT, bool BCAST, int NG, bool LONGROWS = false>
-__global__ void __launch_bounds__(kPipeThreads, (WINDOW || sizeof(V) > 8) ? 0 : 4)   // products: 4 CTAs/SM must fit the register file
+__global__ void __launch_bounds__(kPipeThreads, (WINDOW || sizeof(V) > 8) ? 0 : (LONGROWS ? 3 : 4))   // products: 4 (long rows: 3) CTAs/SM must fit the register file
 spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
                  const int64_t* __restrict__ indptr, const I* __restrict__ cols,
                  const V* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
@@ -195,24 +203,41 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     // y += A_b x (later column blocks): the old y of this thread's first row is fetched ONE TILE
     // AHEAD (the rows of the next tile are known from the plan), so that its DRAM latency never
     // sits in front of a store
-    auto prefetch_y = [&](int64_t tn) -> V {
-      if (!accumulate || tn >= ntiles) return zero_of<V>();
-      const int64_t rb = tile_row[tn], rl = tile_row[tn + 1];
+    // two-step software pipeline: the row range of the tile AFTER next is fetched from the plan while
+    // the current tile runs, so the address of next tile's y is ready when its load is issued (the
+    // dependent tile_row -> y chain used to cost ~500 exposed cycles per tile in block >= 1 launches)
+    const int64_t tstride = (int64_t)NG * gridDim.x;
+    auto rows_of = [&](int64_t tn, int64_t* rb, int64_t* rl) {
+      if (accumulate && tn < ntiles) { *rb = tile_row[tn]; *rl = tile_row[tn + 1]; }
+      else { *rb = 0; *rl = -1; }
+    };
+    auto fetch_y = [&](int64_t rb, int64_t rl) -> V {
       const int64_t nrn = rl - rb + 1;
+      if (!accumulate || nrn <= 0) return zero_of<V>();
       const int ln = lanes_for(nrn, GT);
       const int64_t slot = gtid / ln;
       if ((gtid & (ln - 1)) == 0 && slot < nrn && rb + slot < nrows) return y[rb + slot];
       return zero_of<V>();
     };
-    V ynext = prefetch_y((int64_t)blockIdx.x + (int64_t)grp * gridDim.x);
+    const int64_t tfirst = (int64_t)blockIdx.x + (int64_t)grp * gridDim.x;
+    int64_t rb1, rl1, rb2, rl2;            // row ranges of the next tile and of the one after it
+    rows_of(tfirst, &rb1, &rl1);
+    V ynext = fetch_y(rb1, rl1);
+    rows_of(tfirst + tstride, &rb1, &rl1);
+#ifdef B2S_PIPE_TIMING
+    long long _tprev = clock64();
+#endif
     for (int64_t i = grp; ; i += NG) {
       const int64_t t = (int64_t)blockIdx.x + i * (int64_t)gridDim.x;
       if (t >= ntiles) break;
       const V ypre = ynext;
-      ynext = prefetch_y(t + (int64_t)NG * gridDim.x);
+      rows_of(t + 2 * tstride, &rb2, &rl2);    // plan entries of the tile after next (consumed next iteration)
+      ynext = fetch_y(rb1, rl1);                // old y of the next tile's rows (address known since last iteration)
       const int s = (int)(i % STAGES);
       const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+      B2S_T(0);
       mbar_wait(&full_bar[s], ph);
+      B2S_T(1);
       unsigned char* st = smem + STAGE * s;
       V* svals = reinterpret_cast<V*>(st + L::vals_off);
       const I* scols = reinterpret_cast<const I*>(st + L::cols_off);
@@ -242,6 +267,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           }
         }
       }
+      B2S_T(2);
       if (meta.full_tile) {
         // Gathers are issued in batches of BCH chunks = 4 gathers per thread.  Measured on the
         // column-blocked C2 matrix (profiles/r2_pipe_sweep.txt): all 8 of a thread at once 2.40 ms,
@@ -289,7 +315,9 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           svals[p - S] = vmul(a, ld_gather_na<V>(x + c, pol_keep));
         }
       }
+      B2S_T(3);
       if constexpr (NG == 1) consumer_bar_sync(); else group_bar_sync<GT>(grp);
+      B2S_T(4);
       // slot of the group's PREVIOUS tile = slot of its tile after next: every warp has left the
       // previous tile (it is past this barrier), and nobody appends for the tile after next before
       // the NEXT barrier, which this thread reaches only after this store
@@ -332,6 +360,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         const V sum = group_reduce(vadd(s0, s1), lanes);
         if (valid && gl == 0 && !defer) finish_row(r, lo_g, sum, (accumulate && base != 0) ? y[r] : ypre);
       }
+      B2S_T(5);
       if constexpr (LONGROWS) {
         const int nlong = lr_count[grp][slot];   // complete since the barrier above
         const int wid = gtid >> 5, lane = gtid & 31;
@@ -353,6 +382,8 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
           if (lane == 0) finish_row(r, lo_g, sum, accumulate ? y[r] : zero_of<V>());
         }
       }
+      B2S_T(6);
+      rb1 = rb2; rl1 = rl2;   // rotate at the END of the tile: the plan loads issued at its top have landed
       // the product stores above are generic-proxy writes to memory the TMA refills later: the
       // cross-proxy fence is issued ONCE, by the producer, after it has acquired this arrival
       // (fence.proxy.async = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: 4 % of the kernel when all 256
