@@ -34,6 +34,10 @@ __device__ unsigned long long g_pipe_phase[16];
 #define B2S_T(k) do { } while (0)
 #endif
 
+#ifndef B2S_LONGROW_FACTOR
+#define B2S_LONGROW_FACTOR 32
+#endif
+constexpr int kLongRowFactor = B2S_LONGROW_FACTOR;   // rows longer than this x (lanes per row) get a warp of their own
 constexpr int kPipeConsumers = 256;
 constexpr int kPipeThreads   = kPipeConsumers + 32;
 constexpr int kPipeWinCap    = 1024;  // x-window capacity per stage (elements)
@@ -116,7 +120,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
   uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + STAGE * STAGES);
   uint64_t* empty_bar = full_bar + STAGES;
   __shared__ V wsum[kPipeConsumers / 32];  // DOT only
-  constexpr int LRCAP = LONGROWS ? TILE / 32 + 2 : 1;
+  constexpr int LRCAP = LONGROWS ? TILE / kLongRowFactor + 2 : 1;
   __shared__ int lr_count[NG][3];
   __shared__ int lr_list[NG][3][LRCAP];     // deferred rows (index inside the tile), per group; 3 slots in rotation
 
@@ -261,7 +265,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
               int64_t lo_g, hi_g;
               if (meta.rows_staged) { lo_g = srptr[r - meta.ra]; hi_g = srptr[r - meta.ra + 1]; }
               else                  { lo_g = indptr[r];          hi_g = indptr[r + 1]; }
-              if (min(hi_g, E) - max(lo_g, S) > 32 * lanes)
+              if (min(hi_g, E) - max(lo_g, S) > kLongRowFactor * lanes)
                 lr_list[grp][slot][atomicAdd(&lr_count[grp][slot], 1)] = (int)(base + gtid / lanes);
             }
           }
@@ -345,7 +349,7 @@ spmv_pipe_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
         const int lo = (int)(max(lo_g, S) - S);
         int hi = (int)(min(hi_g, E) - S);
         bool defer = false;
-        if (LONGROWS && lanes < 32 && hi - lo > 32 * lanes) {   // uniform over the lane group; on the list already
+        if (LONGROWS && lanes < 32 && hi - lo > kLongRowFactor * lanes) {   // uniform over the lane group; on the list already
           defer = true;
           hi = lo;   // nothing to add here; every lane still takes part in the shuffles below
         }
