@@ -40,7 +40,9 @@ struct PlanHeader {  // host-side plan object
   int64_t  max_row;    // longest row (nnz) — selects the long-row pass of the products consumer
   int64_t  near_tiles; // tiles whose [min col, max col] image is <= kNearSpan elements: their x gathers
                        // re-hit L1 (products consumer then allocates the gathers in L1)
-  int64_t* counters;   // [4]
+  int64_t  max_tile_rows; // most rows any tile touches (incl. empty ones): the async-gather kernel marks row
+                          // starts with 16-bit tile-local row numbers
+  int64_t* counters;   // [8]
 };
 
 }  // namespace b2s
@@ -109,6 +111,7 @@ __global__ void plan_tile_window_kernel(int64_t nnz, int64_t ntiles, int64_t til
     if (mn >= 0 && mx - mn < kNearSpan) atomicAdd((unsigned long long*)&counters[4], 1ull);
     int64_t r0 = tile_row[t];
     if (indptr[r0] < S) atomicAdd((unsigned long long*)&counters[1], 1ull);
+    atomicMax((unsigned long long*)&counters[5], (unsigned long long)(tile_row[t + 1] - r0 + 1));
   }
 }
 
@@ -346,6 +349,7 @@ spmv_rowvec_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const I* _
 
 }  // namespace b2s
 #include "b2s_spmv_pipe.cuh"
+#include "b2s_spmv_agather.cuh"
 namespace b2s {
 
 // ------------------------------------------------------------------ host launchers
@@ -435,6 +439,36 @@ static int launch_pipe_inst(const PlanHeader* P, const int64_t* indptr, const I*
   return B2S_OK;
 }
 
+// async-gather kernel (b2s_spmv_agather.cuh): plain y = A x / y += A x on 1024-nnz tiles, 4- and 8-byte values
+template <typename V, typename I>
+static int launch_agather_inst(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
+                               const V* x, V* y, int64_t* npartials, int accumulate, cudaStream_t st) {
+  using L = AgLayout<V>;
+  const size_t smem = L::total;
+  auto kern = spmv_agather_kernel<V, I>;
+  static std::atomic<int> max_blocks_per_sm[kMaxDevices];
+  const int dev = current_device();
+  int nb_max = max_blocks_per_sm[dev].load(std::memory_order_acquire);
+  if (nb_max <= 0) {
+    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2S_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    B2S_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, kern, kPipeThreads, smem));
+    if (nb_max < 1) { set_error("spmv_agather_kernel does not fit on an SM (smem %zu)", smem); return B2S_ERR_CUDA; }
+    max_blocks_per_sm[dev].store(nb_max, std::memory_order_release);
+  }
+  int nb = nb_max;
+  const int cap = env_int("B2S_SPMV_CTAS", 0);
+  if (cap >= 1 && cap < nb) nb = cap;
+  int64_t grid = (int64_t)nb * num_sms();
+  if (grid > P->ntiles) grid = P->ntiles;
+  *npartials = grid;
+  kern<<<(unsigned)grid, kPipeThreads, smem, st>>>(P->nrows, P->ncols, P->nnz, P->ntiles, indptr, cols, vals, x, y,
+                                                  (const int64_t*)P->tile_row, reinterpret_cast<V*>(P->head),
+                                                  accumulate ? 1 : 0);
+  B2S_CHECK_LAUNCH();
+  return B2S_OK;
+}
+
 template <typename V, typename I, int TILE, bool DOT>
 static int launch_pipe_tile(const PlanHeader* P, const int64_t* indptr, const I* cols, const V* vals,
                             const V* x, V* y, V* dot_partials, const V* w, int64_t* npartials,
@@ -451,6 +485,16 @@ static int launch_pipe_tile(const PlanHeader* P, const int64_t* indptr, const I*
   // small lane group — give those rows a warp each in a second pass (plain SpMV instances only)
   bool longrows = P->max_row > 64 && P->max_row * P->nrows > 8 * P->nnz;
   longrows = env_int("B2S_SPMV_LONGROWS", longrows ? 1 : 0) != 0;
+  if constexpr (!DOT && TILE == 1024 && sizeof(V) <= 8) {
+    // skewed rows: the async-gather kernel (segmented sum, next tile's gathers in flight during the
+    // reduction).  B2S_SPMV_AGATHER=0 falls back to the long-row pass of the products consumer, =1 forces
+    // the kernel for every gathered (non-window) matrix.
+    const int ag = env_int("B2S_SPMV_AGATHER", -1);
+    if (!bcast && P->max_tile_rows <= 65535 && P->nrows > 0 && (uintptr_t)x % 16 == 0 &&
+        (ag == 1 || (ag != 0 && longrows))) {
+      return launch_agather_inst<V, I>(P, indptr, cols, vals, x, y, npartials, accumulate, st);
+    }
+  }
   if constexpr (!DOT && TILE == 1024) {
     if (longrows && !bcast)
       return launch_pipe_inst<V, I, TILE, 2, false, false, false, 2, true>(P, indptr, cols, vals, x, y, dot_partials, w,
@@ -676,7 +720,7 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
     P->tile_win = reinterpret_cast<int64_t*>(base);               base += nt * 16;
     P->head = reinterpret_cast<void*>(base);                      base += nt * 16;
     P->dotp = reinterpret_cast<void*>(base);                      base += nt * 16;
-    P->empty_rows = 0; P->max_row = 0; P->near_tiles = 0;
+    P->empty_rows = 0; P->max_row = 0; P->near_tiles = 0; P->max_tile_rows = 0;
     if (nt == 0) break;
     cudaError_t e = cudaMemsetAsync(P->counters, 0, 64, st);
     if (e != cudaSuccess) { delete P; set_error("memset failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
@@ -697,9 +741,9 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
       plan_count_empty_kernel<<<(unsigned)blocks, 256, 0, st>>>(nrows, indptr, P->counters);
       g_launch_count.fetch_add(1);
     }
-    int64_t h[5] = {0, 0, 0, 0, 0};
+    int64_t h[6] = {0, 0, 0, 0, 0, 0};
     e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 40, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, P->counters, 48, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { delete P; set_error("plan build failed: %s", cudaGetErrorString(e)); return B2S_ERR_CUDA; }
     P->window_tiles = h[0];
@@ -707,6 +751,7 @@ int plan_create_impl(b2s_itype it, int64_t nrows, int64_t ncols, int64_t nnz,
     P->empty_rows = h[2];
     P->max_row = h[3];
     P->near_tiles = h[4];
+    P->max_tile_rows = h[5];
     if (forced || P->window_tiles * 2 >= P->ntiles) break;   // keep this tiling
   }
   *out_plan = P;

@@ -12,6 +12,8 @@
 //   bulk16     one 16-byte cp.async.bulk (UBLKCP) per element
 //   mix        8 LSU warps gather (2048-TM) elements of every 2048-element tile themselves while a
 //              producer warp stages the other TM through gather4 — both request paths at once
+//   ldgsts     cp.async.ca.shared.global 8-byte gathers (LDGSTS): the LSU request path, but the data lands in
+//              shared memory without holding a destination register while in flight
 //   dsmem      x slice spread over the shared memory of a thread-block cluster (8 or 16 CTAs),
 //              ld.shared::cluster gathers (no L1TEX tag stage, no L2)
 //
@@ -151,6 +153,67 @@ __global__ void __launch_bounds__(256) k_lsu_mode(int64_t nnz, const int* __rest
 #pragma unroll
     for (int u = 0; u < U; ++u) acc += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
   }
+  block_sum_to(acc, out);
+}
+
+// ---------------------------------------------------------------- ldgsts: cp.async (LDGSTS) 8-byte gathers straight into shared memory
+// No destination register is held while the gather is in flight: DEPTH commit groups of 4 gathers per
+// thread are outstanding, the thread reads its own 4 slots back (2 x LDS.128) once the oldest group landed.
+template <int DEPTH, bool CG16>
+__global__ void __launch_bounds__(256) k_ldgsts(int64_t nnz, const int* __restrict__ cols, const double* __restrict__ x, double* out) {
+  // CG16: cp.async.cg 16 bytes (LDGSTS.E.BYPASS.128) of the aligned pair that holds the element — the only
+  // cp.async form that does not allocate an L1 line per request in flight; the 8-byte form is .ca only
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int SL = CG16 ? 2 : 1;                          // doubles per slot
+  double* ring = reinterpret_cast<double*>(smem);          // [DEPTH][1024 * SL]
+  double acc = 0;
+  const int tid = threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + tid) * 4;
+  int it = 0;
+  unsigned par[DEPTH];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) par[d] = 0;
+  auto consume = [&](int k) {
+    const double* r = ring + ((k % DEPTH) * 1024 + tid * 4) * SL;
+    if (CG16) {
+      unsigned pm = 0;
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) if (d == k % DEPTH) pm = par[d];
+      acc += (r[0 + (pm & 1)] + r[2 + ((pm >> 1) & 1)]) + (r[4 + ((pm >> 2) & 1)] + r[6 + ((pm >> 3) & 1)]);
+    } else {
+      const double2 a = *reinterpret_cast<const double2*>(r), b = *reinterpret_cast<const double2*>(r + 2);
+      acc += (a.x + a.y) + (b.x + b.y);
+    }
+  };
+  for (; i + 3 < nnz; i += stride, ++it) {
+    const int4 c = ldg_stream4(cols + i);
+    double* slot = ring + ((it % DEPTH) * 1024 + tid * 4) * SL;
+    const uint32_t d = smem_u32(slot);
+    if (CG16) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(x + (c.x & ~1)) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(x + (c.y & ~1)) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 32), "l"(x + (c.z & ~1)) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 48), "l"(x + (c.w & ~1)) : "memory");
+      const unsigned pm = (c.x & 1) | ((c.y & 1) << 1) | ((c.z & 1) << 2) | ((c.w & 1) << 3);
+#pragma unroll
+      for (int q = 0; q < DEPTH; ++q) if (q == it % DEPTH) par[q] = pm;
+    } else {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(x + c.x) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8), "l"(x + c.y) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 16), "l"(x + c.z) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 24), "l"(x + c.w) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (it >= DEPTH - 1) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+      // the group consumed here was issued DEPTH-1 iterations ago; its parity mask is still in par[]
+      // only when DEPTH > 1 slots are distinct — consume before this iteration's mask overwrote it
+      consume(it - (DEPTH - 1));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  for (int k = (it >= DEPTH - 1 ? it - (DEPTH - 1) : 0); k < it; ++k) consume(k);
   block_sum_to(acc, out);
 }
 
@@ -392,6 +455,28 @@ int main(int argc, char** argv) {
   run("lsu   ld.global.nc.f64  unroll 4 (16 in flight)", nnz, iters, ref_sum, [&] { k_lsu<4, false><<<148 * 8, 256>>>(nnz, cols, x, d_out); });
   run("lsu   unroll 2, 4 CTAs/SM", nnz, iters, ref_sum, [&] { k_lsu<2, false><<<148 * 4, 256>>>(nnz, cols, x, d_out); });
   run("lsu16 ld.global.nc.v2.f64 unroll 2", nnz, iters, ref_sum, [&] { k_lsu<2, true><<<148 * 8, 256>>>(nnz, cols, x, d_out); });
+
+  // ---- cp.async (LDGSTS) gathers into shared memory: DEPTH x 4 gathers per thread in flight, no registers held.
+  // `smem KB/SM` is what the resident CTAs allocate: the driver sizes the L1 with what is left of 256 KB, and the
+  // 8-byte form (.ca) needs an L1 line per request in flight, the 16-byte form (.cg) does not.
+  {
+    auto go = [&](auto kern, const char* what, int depth, int ctas, size_t pad_kb) {
+      size_t sm = (size_t)depth * 8192 * (strstr(what, "cg") ? 2 : 1) + pad_kb * 1024;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      char name[128]; snprintf(name, sizeof name, "ldgsts %s, %2d in flight/thread, CTAs/SM=%d, smem %3zu KB/SM", what, depth * 4, ctas, sm * ctas / 1024);
+      run(name, nnz, iters, ref_sum, [&] { kern<<<148 * ctas, 256, sm>>>(nnz, cols, x, d_out); });
+    };
+    for (int ctas : {2, 4}) {
+      for (size_t pad : {(size_t)0, (size_t)32}) {
+        go(k_ldgsts<2, false>, "ca  8 B", 2, ctas, pad);
+        go(k_ldgsts<2, true>,  "cg 16 B", 2, ctas, pad);
+      }
+    }
+    go(k_ldgsts<1, false>, "ca  8 B", 1, 4, 0);
+    go(k_ldgsts<1, true>,  "cg 16 B", 1, 4, 0);
+    if (getenv("GATHER_LDGSTS_ONLY")) return 0;
+  }
 
   // ---- load flavours x requests in flight x CTAs/SM (matters when x misses L2: run with xmb = 64 / 160)
   if (getenv("GATHER_FLAVOURS")) {
