@@ -20,9 +20,10 @@
 //   * the reduction is a SEGMENTED SUM in nnz order: a thread owns 4 consecutive products
 //     (val * x read back from shared memory), rows are delimited by per-element row-start marks, rows
 //     that end inside a thread are stored at once, open pieces are combined by a warp-level segmented
-//     scan (ballot + 5 shuffle steps) and one exchange between the 8 warps.  Work per tile is the same
-//     whatever the row-length distribution: no lane walks a long row alone, no separate long-row
-//     pass, one CTA barrier per tile.
+//     scan (ballot + 5 shuffle steps) and one exchange between the 8 warps through shared memory
+//     (release / acquire on a per-warp sequence number — only a thread whose row runs past its warp
+//     waits; no CTA barrier in the loop).  Work per tile is the same whatever the row-length
+//     distribution: no lane walks a long row alone, no separate long-row pass.
 //   * the column ids and values of a tile are read by the thread that uses them (16 / 32 coalesced bytes,
 //     ld.global.nc.L1::no_allocate, L2 evict_first) one tile AHEAD into registers: staging them in
 //     shared memory as spmv_pipe_kernel does left too little of it for the 16 bytes per element the
@@ -137,8 +138,13 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
   uint64_t* fullR  = reinterpret_cast<uint64_t*>(rring + RSLOT * NR);   // row pointers of a slot have landed
   uint64_t* marksB = fullR + NR;                                        // marks of a slot are written
   uint64_t* emptyM = marksB + NM;                                       // marks of a slot are consumed (and cleared)
-  __shared__ V   wsum[2][NW];    // per warp: sum of the leading open piece (up to the warp's first row start)
-  __shared__ int wany[2][NW];    // per warp: does a row start inside the warp's 128 elements
+  // Per-warp summaries of a tile, exchanged WITHOUT a CTA barrier: a warp publishes {sum of its leading open
+  // piece, "a row starts inside my 128 elements"} and then the tile's sequence number (release); only a thread
+  // whose row runs past the end of its warp waits (acquire) for the summaries of the following warps.  Four
+  // buffers in rotation: the marks ring keeps the warps of a CTA within 3 tiles of each other.
+  __shared__ V   wsum[4][NW];
+  __shared__ int wany[4][NW];
+  __shared__ int wseq[4][NW];
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -146,6 +152,7 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     for (int s = 0; s < NM; ++s) { mbar_init(&marksB[s], 32); mbar_init(&emptyM[s], GT); }
     fence_mbar_init();
   }
+  if (tid < 4 * NW) (&wseq[0][0])[tid] = 0;
   if (tid < GT) {   // row-start marks start out clear; afterwards every consumer clears what it has read
     for (int s = 0; s < NM; ++s) reinterpret_cast<uint2*>(mring + MSLOT * s)[tid] = make_uint2(0, 0);
   }
@@ -335,28 +342,44 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     V Gn = vshfl_down(G, 1);
     if (lane == 31) Gn = zero_of<V>();
     const bool anyn = (above >> 1) != 0u;   // a row starts in a later lane of this warp
-    if (lane == 0) { wsum[i & 1][w] = G; wany[i & 1][w] = above != 0u ? 1 : 0; }
+    if (lane == 0) {
+      wsum[i & 3][w] = G; wany[i & 3][w] = above != 0u ? 1 : 0;
+      asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(&wseq[i & 3][w])), "r"(i + 1) : "memory");
+    }
     // the open tail of this thread's last row: closed inside the warp -> store now
     V tail = zero_of<V>();
     if (has) {
       tail = vadd(acc, Gn);
       if (anyn) store_row(cur, tail);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");   // warp summaries of tile i
+    // summary of warp v for tile i (waits until that warp has published it)
+    auto summary_of = [&](int v, V* sum) -> bool {
+      const uint32_t a = smem_u32(&wseq[i & 3][v]);
+      int sq;
+      do { asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(sq) : "r"(a) : "memory"); } while (sq != i + 1);
+      *sum = wsum[i & 3][v];
+      return wany[i & 3][v] != 0;
+    };
     if (has && !anyn) {
       // the row runs on into the following warps (or past the tile: then this is the owner's piece and
       // spmv_fixup_kernel adds the heads of the later tiles)
       for (int v = w + 1; v < NW; ++v) {
-        tail = vadd(tail, wsum[i & 1][v]);
-        if (wany[i & 1][v]) break;
+        V sv;
+        const bool stop = summary_of(v, &sv);
+        tail = vadd(tail, sv);
+        if (stop) break;
       }
       store_row(cur, tail);
     }
     if (g == 0 && head_cur) {
-      V h = zero_of<V>();
-      for (int v = 0; v < NW; ++v) {
-        h = vadd(h, wsum[i & 1][v]);
-        if (wany[i & 1][v]) break;
+      V h = G;                     // warp 0's own leading piece (this is lane 0 of warp 0)
+      if (above == 0u) {
+        for (int v = 1; v < NW; ++v) {
+          V sv;
+          const bool stop = summary_of(v, &sv);
+          h = vadd(h, sv);
+          if (stop) break;
+        }
       }
       head[t] = h;
     }
