@@ -241,28 +241,54 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
   const int g = tid, w = tid >> 5, lane = tid & 31;
   constexpr int PER16 = 16 / (int)sizeof(V);          // x elements per 16-byte chunk (2 or 4)
 
+  using U = typename std::make_unsigned<I>::type;
+  const U ncols_whole = (U)(ncols & ~(int64_t)(PER16 - 1));   // columns below this lie in a whole 16-byte chunk of x
+  // byte offset of the thread's k-th 16-byte slot inside an x slot (ag_own_slot), fixed for the kernel's lifetime
+  uint32_t xoff[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) xoff[k] = 16u * (uint32_t)ag_own_slot(g, k);
+  const uint32_t xring_s = smem_u32(xring);
+
   // Issue the thread's 4 x gathers of a tile (column ids c[], -1 = padding) into x slot `xs`.  Element k lands
   // as the aligned 16-byte chunk of x that holds it; the return value packs, 2 bits per element, which
   // sizeof(V)-sized piece of the chunk it is.
   auto issue = [&](int xs, const I c[4]) -> int {
-    unsigned char* sxq = xring + XSLOT * xs;
+    const uint32_t sx = xring_s + (uint32_t)XSLOT * (uint32_t)xs;
     int sub = 0;
+    if ((U)c[0] < ncols_whole && (U)c[1] < ncols_whole && (U)c[2] < ncols_whole && (U)c[3] < ncols_whole) {
+      // the common case: four L1-bypassing 16-byte copies, issued back to back
+      const char* s0 = reinterpret_cast<const char*>(x) + (size_t)((U)c[0] & ~(U)(PER16 - 1)) * sizeof(V);
+      const char* s1 = reinterpret_cast<const char*>(x) + (size_t)((U)c[1] & ~(U)(PER16 - 1)) * sizeof(V);
+      const char* s2 = reinterpret_cast<const char*>(x) + (size_t)((U)c[2] & ~(U)(PER16 - 1)) * sizeof(V);
+      const char* s3 = reinterpret_cast<const char*>(x) + (size_t)((U)c[3] & ~(U)(PER16 - 1)) * sizeof(V);
+      asm volatile(
+          "cp.async.cg.shared.global.L2::cache_hint [%0], [%4], 16, %8;\n"
+          "cp.async.cg.shared.global.L2::cache_hint [%1], [%5], 16, %8;\n"
+          "cp.async.cg.shared.global.L2::cache_hint [%2], [%6], 16, %8;\n"
+          "cp.async.cg.shared.global.L2::cache_hint [%3], [%7], 16, %8;\n"
+          "cp.async.commit_group;" ::"r"(sx + xoff[0]), "r"(sx + xoff[1]), "r"(sx + xoff[2]), "r"(sx + xoff[3]),
+          "l"(s0), "l"(s1), "l"(s2), "l"(s3), "l"(pol_keep)
+          : "memory");
+      sub = (int)(c[0] & (PER16 - 1)) | ((int)(c[1] & (PER16 - 1)) << 2) | ((int)(c[2] & (PER16 - 1)) << 4) |
+            ((int)(c[3] & (PER16 - 1)) << 6);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      unsigned char* slot = sxq + 16 * ag_own_slot(g, k);
-      const int64_t ck = (int64_t)c[k];
-      if (ck < 0) {                                              // padding of the partial tile
-        *reinterpret_cast<V*>(slot) = zero_of<V>();
-      } else if ((ck | (PER16 - 1)) < ncols) {                   // the whole chunk lies inside x
-        cp_async_gather16_bypass(smem_u32(slot), x + (ck & ~(int64_t)(PER16 - 1)), pol_keep);
-        sub |= (int)(ck & (PER16 - 1)) << (2 * k);
-      } else {                                                   // last, short chunk of x: the element alone
-        cp_async_gather<(int)sizeof(V)>(smem_u32(slot), x + ck, pol_keep);
+      for (int k = 0; k < 4; ++k) {
+        unsigned char* slot = xring + XSLOT * xs + xoff[k];
+        if (c[k] < 0) {                                            // padding of the partial tile
+          *reinterpret_cast<V*>(slot) = zero_of<V>();
+        } else if ((U)c[k] < ncols_whole) {                        // the whole chunk lies inside x
+          cp_async_gather16_bypass(smem_u32(slot), x + ((int64_t)c[k] & ~(int64_t)(PER16 - 1)), pol_keep);
+          sub |= (int)(c[k] & (PER16 - 1)) << (2 * k);
+        } else {                                                   // last, short chunk of x: the element alone
+          cp_async_gather<(int)sizeof(V)>(smem_u32(slot), x + (int64_t)c[k], pol_keep);
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     return sub;
   };
+
   auto tile_span = [&](int j, int64_t* S, int64_t* E) {
     *S = ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * (int64_t)T;
     *E = min(*S + (int64_t)T, nnz);
@@ -303,7 +329,7 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     const unsigned char* sxq = xring + XSLOT * (i & 1);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      xv[k] = *reinterpret_cast<const V*>(sxq + 16 * ag_own_slot(g, k) + sizeof(V) * ((sub >> (2 * k)) & 3));
+      xv[k] = *reinterpret_cast<const V*>(sxq + xoff[k] + sizeof(V) * ((sub >> (2 * k)) & 3));
     uint2* mk = reinterpret_cast<uint2*>(msl) + g;
     const uint2 mraw = *mk;
     *mk = make_uint2(0, 0);                 // clear what this thread consumed (re-marked 3 tiles later)
@@ -311,8 +337,9 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     if (++ms == NM) { ms = 0; mp ^= 1u; }
     const int id[4] = {(int)(mraw.x & 0xffffu), (int)(mraw.x >> 16), (int)(mraw.y & 0xffffu), (int)(mraw.y >> 16)};
 
+    V* const yrow = y + (r_begin - 1);      // y of the tile's row number rid (1-based): yrow[rid]
     auto store_row = [&](int rid, V sum) {
-      V* dst = y + (r_begin + (rid - 1));
+      V* dst = yrow + rid;
       if (accumulate) sum = vadd(sum, *dst);
       st_stream<V>(dst, sum, pol_stream);
     };

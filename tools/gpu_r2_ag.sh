@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_agather.py -m gpu -x -q 2>&1 | tail -15
 (
-for cfg in "AGATHER=0" "AGATHER=1" "AGATHER=1 B2S_SPMV_CTAS=3" "AGATHER=1 B2S_SPMV_CTAS=2"; do
+for cfg in "AGATHER=1" "AGATHER=1 B2S_SPMV_CTAS=3"; do
   echo "=== powerlaw B2S_SPMV_$cfg"
   env B2S_SPMV_$cfg timeout 120 python tools/side_bench.py powerlaw 2>/dev/null | head -1 | cut -c1-420
 done
