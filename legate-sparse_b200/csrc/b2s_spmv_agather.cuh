@@ -256,7 +256,9 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     const uint32_t sx = xring_s + (uint32_t)XSLOT * (uint32_t)xs;
     int sub = 0;
     if ((U)c[0] < ncols_whole && (U)c[1] < ncols_whole && (U)c[2] < ncols_whole && (U)c[3] < ncols_whole) {
-      // the common case: four L1-bypassing 16-byte copies, issued back to back
+      // the common case: four L1-bypassing 16-byte copies, issued back to back.  (Careful with this block: in an
+      // experimental variant of the kernel ptxas 12.9 encoded such copies as LDGSTS [R+UR0], desc[UR1] with
+      // UR0/UR1 never written -> "illegal instruction" at run time; the Makefile greps the SASS for that form.)
       const char* s0 = reinterpret_cast<const char*>(x) + (size_t)((U)c[0] & ~(U)(PER16 - 1)) * sizeof(V);
       const char* s1 = reinterpret_cast<const char*>(x) + (size_t)((U)c[1] & ~(U)(PER16 - 1)) * sizeof(V);
       const char* s2 = reinterpret_cast<const char*>(x) + (size_t)((U)c[2] & ~(U)(PER16 - 1)) * sizeof(V);

@@ -166,3 +166,18 @@ def test_agather_accumulate_column_blocks(monkeypatch):
     y = A @ x
     assert A._block().colblock not in (None, False)
     assert np.allclose(y, S @ x, rtol=1e-11, atol=1e-11)
+
+
+def test_agather_many_tiles_per_cta(monkeypatch):
+    """one CTA per SM and ~20 tiles per CTA: the software pipeline in steady state and the flow control of the
+    warp-summary buffers (a warp may run at most 8 tiles ahead of the warps that read its summaries)"""
+    force(monkeypatch)
+    monkeypatch.setenv("B2S_SPMV_CTAS", "1")
+    d, c, p = gen.powerlaw_csr(400000, 400000, max_row=20000, seed=5)
+    S = sp.csr_array((d, c, p), shape=(400000, 400000))
+    assert S.nnz > 148 * 1024 * 12
+    x = np.random.default_rng(6).standard_normal(400000)
+    A = sparse.csr_array(S)
+    y = A @ x
+    assert np.allclose(y, S @ x, rtol=1e-10, atol=1e-10)
+    assert np.array_equal(y, A @ x)
