@@ -670,9 +670,11 @@ def spgemm_leg(args, dist, dev, rank):
     nnzA = int(data.numel())
     A = sparse.csr_array((data, idx, ptr), shape=(n, n))
     partition = f"A row-blocked over {G} rank(s) (equal rows), B replicated"
-    if G > 1:
-        # R-MAT rows are skewed: equal-row blocks leave 2/3 of the work on rank 0.  Balance the
-        # intermediate products per rank instead (rows weighted by sum_k nnz(B_k))
+    if G > 2:
+        # R-MAT rows are skewed: equal-row blocks leave 2/3 of C on rank 0 (at scale 20 that is what has to fit).
+        # Balance the intermediate products per rank instead (rows weighted by sum_k nnz(B_k)).  At 2 ranks the
+        # equal-row split is kept: measured 136 ms vs 232 ms product-balanced (profiles/r2_bench_n2.json before /
+        # after) — the heavy rows of the dense-accumulator class, not the products, set the time there.
         row_nnzB = (ptr[1:] - ptr[:-1]).to(torch.float64)
         w = torch.zeros(n, dtype=torch.float64, device=dev)
         rows = torch.repeat_interleave(torch.arange(n, device=dev), (ptr[1:] - ptr[:-1]))
