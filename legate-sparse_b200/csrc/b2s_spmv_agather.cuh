@@ -56,7 +56,7 @@ struct AgVMeta {   // per marks slot, written with the row-start marks
 template <typename V>
 struct AgLayout {
   static constexpr int T = kAgTile;
-  static constexpr int RCAP = T / 4 + 4;             // indptr entries per slot
+  static constexpr int RCAP = 3 * T / 8 + 4;         // indptr entries per slot (388; tiles that touch more rows read indptr from global memory)
   static constexpr int NR = 4;                       // row-pointer slots (private to the row-pointer warp)
   static constexpr int NM = 3;                       // marks slots
   static constexpr size_t xslot_bytes = 16 * T;      // gathered x: 16 bytes per element (the aligned chunk of x), 2 slots
