@@ -58,7 +58,7 @@ struct AgLayout {
   static constexpr int T = kAgTile;
   static constexpr int RCAP = 3 * T / 8 + 4;         // indptr entries per slot (388; tiles that touch more rows read indptr from global memory)
   static constexpr int NR = 4;                       // row-pointer slots (private to the row-pointer warp)
-  static constexpr int NM = 3;                       // marks slots
+  static constexpr int NM = 4;                       // marks slots: the row-pointer warp may run 3 tiles ahead
   static constexpr size_t xslot_bytes = 16 * T;      // gathered x: 16 bytes per element (the aligned chunk of x), 2 slots
   static constexpr size_t vmeta_off   = 2 * T;       // marks slot: uint16 per element + AgVMeta
   static constexpr size_t mslot_bytes = (vmeta_off + sizeof(AgVMeta) + 127) / 128 * 128;
@@ -140,11 +140,13 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
   uint64_t* emptyM = marksB + NM;                                       // marks of a slot are consumed (and cleared)
   // Per-warp summaries of a tile, exchanged WITHOUT a CTA barrier: a warp publishes {sum of its leading open
   // piece, "a row starts inside my 128 elements"} and then the tile's sequence number (release); only a thread
-  // whose row runs past the end of its warp waits (acquire) for the summaries of the following warps.  Four
-  // buffers in rotation: the marks ring keeps the warps of a CTA within 3 tiles of each other.
-  __shared__ V   wsum[4][NW];
-  __shared__ int wany[4][NW];
-  __shared__ int wseq[4][NW];
+  // whose row runs past the end of its warp waits (acquire) for the summaries of the following warps.  kSeq
+  // buffers in rotation: the marks ring keeps the warps of a CTA within NM tiles of each other.
+  constexpr int kSeq = 8;
+  static_assert(kSeq > NM && (kSeq & (kSeq - 1)) == 0, "summary buffers must outnumber the marks slots");
+  __shared__ V   wsum[kSeq][NW];
+  __shared__ int wany[kSeq][NW];
+  __shared__ int wseq[kSeq][NW];
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -152,7 +154,7 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     for (int s = 0; s < NM; ++s) { mbar_init(&marksB[s], 32); mbar_init(&emptyM[s], GT); }
     fence_mbar_init();
   }
-  if (tid < 4 * NW) (&wseq[0][0])[tid] = 0;
+  if (tid < kSeq * NW) (&wseq[0][0])[tid] = 0;
   if (tid < GT) {   // row-start marks start out clear; afterwards every consumer clears what it has read
     for (int s = 0; s < NM; ++s) reinterpret_cast<uint2*>(mring + MSLOT * s)[tid] = make_uint2(0, 0);
   }
@@ -204,7 +206,7 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
       if (lane == 0 && j + NR - 1 < my_tiles) r_tma(j + NR - 1);   // refills the slot of tile j-1
       // Row-start marks of tile j: element (indptr[r] - S) <- 1 + (r - r_begin) for every non-empty row the tile
       // owns; owned EMPTY rows are stored here (no element to carry a mark).
-      mbar_wait(&emptyM[ms], mp ^ 1u);    // tile j-3 is reduced: its marks slot is clear and free
+      mbar_wait(&emptyM[ms], mp ^ 1u);    // tile j-NM is reduced: its marks slot is clear and free
       mbar_wait(&fullR[rs], rp);
       {
         const unsigned char* rsl = rring + RSLOT * rs;
@@ -334,7 +336,7 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
       xv[k] = *reinterpret_cast<const V*>(sxq + xoff[k] + sizeof(V) * ((sub >> (2 * k)) & 3));
     uint2* mk = reinterpret_cast<uint2*>(msl) + g;
     const uint2 mraw = *mk;
-    *mk = make_uint2(0, 0);                 // clear what this thread consumed (re-marked 3 tiles later)
+    *mk = make_uint2(0, 0);                 // clear what this thread consumed (re-marked NM tiles later)
     mbar_arrive(&emptyM[ms]);               // the marks slot is free
     if (++ms == NM) { ms = 0; mp ^= 1u; }
     const int id[4] = {(int)(mraw.x & 0xffffu), (int)(mraw.x >> 16), (int)(mraw.y & 0xffffu), (int)(mraw.y >> 16)};
@@ -372,8 +374,8 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     if (lane == 31) Gn = zero_of<V>();
     const bool anyn = (above >> 1) != 0u;   // a row starts in a later lane of this warp
     if (lane == 0) {
-      wsum[i & 3][w] = G; wany[i & 3][w] = above != 0u ? 1 : 0;
-      asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(&wseq[i & 3][w])), "r"(i + 1) : "memory");
+      wsum[i & (kSeq - 1)][w] = G; wany[i & (kSeq - 1)][w] = above != 0u ? 1 : 0;
+      asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(&wseq[i & (kSeq - 1)][w])), "r"(i + 1) : "memory");
     }
     // the open tail of this thread's last row: closed inside the warp -> store now
     V tail = zero_of<V>();
@@ -383,11 +385,11 @@ spmv_agather_kernel(int64_t nrows, int64_t ncols, int64_t nnz, int64_t ntiles,
     }
     // summary of warp v for tile i (waits until that warp has published it)
     auto summary_of = [&](int v, V* sum) -> bool {
-      const uint32_t a = smem_u32(&wseq[i & 3][v]);
+      const uint32_t a = smem_u32(&wseq[i & (kSeq - 1)][v]);
       int sq;
       do { asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(sq) : "r"(a) : "memory"); } while (sq != i + 1);
-      *sum = wsum[i & 3][v];
-      return wany[i & 3][v] != 0;
+      *sum = wsum[i & (kSeq - 1)][v];
+      return wany[i & (kSeq - 1)][v] != 0;
     };
     if (has && !anyn) {
       // the row runs on into the following warps (or past the tile: then this is the owner's piece and
