@@ -29,11 +29,11 @@
 //     shared memory as spmv_pipe_kernel does left too little of it for the 16 bytes per element the
 //     gathers need (3 CTAs x 1-2 tiles of TMA in flight could not cover the DRAM latency: consumers
 //     waited 23 % of the time for values).  Shared memory holds only the gathered x (2 tiles), the
-//     row-start marks (3 tiles) and the row pointers (4 tiles): 47 KB, 4 CTAs per SM.
+//     row-start marks (4 tiles) and the row pointers (4 tiles): 53 KB, 4 CTAs per SM.
 //   * a ROW-POINTER WARP does everything that needs indptr: lane 0 fetches the tile's slice of
 //     indptr with a TMA bulk copy (4 tiles ahead); then all 32 lanes turn it into row-start marks
 //     (16-bit tile-local row numbers), store the zeros of owned empty rows and publish "marks ready"
-//     on an mbarrier, up to 2 tiles ahead of the reduction.  The other warps never read a row pointer.
+//     on an mbarrier, up to 3 tiles ahead of the reduction.  The other warps never read a row pointer.
 #pragma once
 
 namespace b2s {
