@@ -76,6 +76,10 @@ typedef struct b2s_spmv_plan b2s_spmv_plan; /* opaque, host object */
  *          memory ring by a producer warp; consumers: row-walk (window matrices) or two ping-pong
  *          groups doing products + row reduction (x gathered from L2).  nnz-balanced tiles, rows
  *          that straddle tiles are completed by a fix-up pass (merge-path style decomposition).
+ *          Matrices with skewed row lengths (plan statistic: longest row > 64 and > 8 x the mean; BASELINE
+ *          config 5) run the async-gather kernel instead for plain y = A x / y += A x: x gathered by
+ *          L1-bypassing cp.async one tile ahead, segmented sum in nnz order (b2s_spmv_agather.cuh).
+ *          Same results contract: no floating-point atomics, bit-reproducible run to run.
  * TILE   = one CTA per tile, register-staged 128-bit loads (fallback for unaligned slices)
  * ROWVEC = plan-free 2..32 lanes per row */
 enum { B2S_SPMV_AUTO = 0, B2S_SPMV_ROWVEC = 1, B2S_SPMV_TILE = 2, B2S_SPMV_PIPE = 3 };
